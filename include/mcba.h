@@ -1,0 +1,166 @@
+/* mcba.h -- C ABI of the B200 bundle-adjustment engine (libmcba.so).
+ *
+ * The reference (dattalab-6-cam/multicam-calibration) is pure Python and has no
+ * FFI of its own; the drop-in boundary is the set of Python functions in
+ * multicam_calibration/bundle_adjustment.py and geometry.py.  Each entry point
+ * below names the reference function (file:line under /root/reference/
+ * multicam_calibration/) whose arithmetic it replaces; INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success or a negative MCBA_ERR_* code (mcba_last_error() gives the text); no
+ * exceptions cross the boundary; buffers are caller-owned; a handle is bound to
+ * one CUDA device and one stream and is not thread-safe.  Pointers named d_*
+ * are DEVICE pointers, h_* are HOST pointers.  All floating point is float64.
+ *
+ * Parameter vector x (bundle_adjustment.py:128-157): per camera
+ * [fx fy cx cy k1 k2 rx ry rz tx ty tz] (12), then per frame [rho(3) tau(3)].
+ * Observations: (C, F, N, 2) row-major, NaN = missing (bundle_adjustment.py:82-84).
+ */
+#ifndef MCBA_H_
+#define MCBA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCBA_OK 0
+#define MCBA_ERR_ARG (-1)
+#define MCBA_ERR_CUDA (-2)
+#define MCBA_ERR_SOLVER (-3)
+#define MCBA_ERR_NONFINITE (-4) /* residuals not finite at x0 (scipy least_squares.py:946) */
+#define MCBA_ERR_NCCL (-5)
+#define MCBA_ERR_STATE (-6)
+
+#define MCBA_LOSS_LINEAR 0
+#define MCBA_LOSS_SOFT_L1 1
+
+typedef struct mcba_handle mcba_handle;
+
+/* Options of the Levenberg-Marquardt loop; field names follow the keyword
+ * arguments bundle_adjust forwards to scipy.optimize.least_squares
+ * (bundle_adjustment.py:301-313).  Termination tests follow scipy
+ * optimize/_lsq/common.py:705-717 and trf.py:466-468. */
+typedef struct mcba_options {
+  double ftol;      /* default 1e-4 (bundle_adjustment.py:302) */
+  double xtol;      /* scipy default 1e-8 */
+  double gtol;      /* scipy default 1e-8 */
+  int32_t max_nfev; /* <= 0: 100 * n (scipy default for trf) */
+  int32_t loss;     /* MCBA_LOSS_* ; reference default soft_l1 */
+  double f_scale;   /* scipy default 1.0 */
+  int32_t verbose;  /* 0 silent, 1 summary, 2 per-iteration table (reference default 2) */
+  int32_t reserved;
+  double lambda0;   /* initial damping, relative to the Jacobian scaling; <= 0: 1e-3 */
+  double lambda_min;
+  double lambda_max;
+  /* Called once per accepted/rejected iteration when non-NULL (the host side
+   * prints scipy's verbose=2 table from it, trf.py:556-558). */
+  void (*iter_callback)(void* user, int iteration, int nfev, double cost, double cost_reduction,
+                        double step_norm, double optimality);
+  void* callback_user;
+} mcba_options;
+
+typedef struct mcba_result {
+  double cost;       /* 0.5 * sum rho(f^2) at the solution */
+  double cost0;      /* at x0 */
+  double optimality; /* ||g||_inf */
+  double rms;        /* sqrt(mean f^2) over finite scalar residuals, px */
+  double step_norm;  /* last accepted ||dx|| */
+  double lambda;     /* final damping */
+  double solve_ms;   /* device time of the loop (CUDA events) */
+  int64_t n_residuals;
+  int32_t nfev;
+  int32_t njev;
+  int32_t iterations;
+  int32_t status; /* scipy codes: 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 ftol+xtol, -1 failure */
+  int64_t kernel_launches;
+} mcba_result;
+
+const char* mcba_last_error(void);
+int mcba_version(void);
+void mcba_default_options(mcba_options* opt);
+
+/* One handle per (device, problem shape). n_frames is THIS rank's frame count. */
+int mcba_create(mcba_handle** out, int n_cameras, int64_t n_frames, int n_points, int device);
+int mcba_destroy(mcba_handle* h);
+/* Run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = handle-owned stream. */
+int mcba_set_stream(mcba_handle* h, void* cuda_stream);
+int mcba_synchronize(mcba_handle* h);
+
+/* Observations (C,F,N,2) + board points (N,3); host or device pointers
+ * (is_device != 0).  Builds the frame-tiled layout the kernels stream and the
+ * row offsets of the NaN compaction of bundle_adjustment.py:97. */
+int mcba_set_observations(mcba_handle* h, const double* uvs, const double* objpoints, int is_device);
+int mcba_num_residuals(mcba_handle* h, int64_t* m, int64_t* n_observations);
+
+/* bundle_adjustment.py:66-98  residuals(params, uvs, objpoints): d_r has m entries,
+ * C order over (c,f,n,uv) with NaN observations removed element-wise. */
+int mcba_residuals(mcba_handle* h, const double* d_x, double* d_r);
+/* bundle_adjustment.py:33-63  predict_calib_uvs: d_uv is (C,F,N,2). */
+int mcba_predict(mcba_handle* h, const double* d_x, double* d_uv);
+/* Analytic replacement of the finite-difference Jacobian (scipy _numdiff.py:288 through
+ * jac_sparsity, bundle_adjustment.py:101-125,310): per (c,f,n) blocks of the RESIDUAL
+ * Jacobian, d_Jc (C,F,N,2,12) w.r.t. camera c, d_Jp (C,F,N,2,6) w.r.t. frame f.
+ * Debug / parity path. */
+int mcba_jacobian_blocks(mcba_handle* h, const double* d_x, double* d_Jc, double* d_Jp);
+/* 0.5*sum rho, sum f^2, count at x (scipy least_squares.py:226-252 loss_function cost_only). */
+int mcba_cost(mcba_handle* h, const double* d_x, int loss, double f_scale, double* h_cost,
+              double* h_sumsq, int64_t* h_count);
+
+/* Residual + analytic Jacobian + robust scaling + Schur elimination of the
+ * pose blocks in one pass: reduced camera system S (12C x 12C, row major),
+ * b (12C), the camera gradient and cost, with pose damping lambda * D_f^2 folded
+ * in and NO camera damping (added by the solve).  Replaces scipy trf's
+ * J / LSMR machinery (trf.py:415-587).  Outputs are HOST pointers (may be NULL). */
+int mcba_build_reduced(mcba_handle* h, const double* d_x, double lambda, int loss, double f_scale,
+                       double* h_S, double* h_b, double* h_gcam, double* h_cost);
+/* Same, through HOST buffers end to end: uploads uvs (C,F,N,2) and x, runs the
+ * pass, downloads S, b.  This is the call bench.py times as "e2e". */
+int mcba_build_reduced_host(mcba_handle* h, const double* h_uvs, const double* h_objpoints,
+                            const double* h_x, double lambda, int loss, double f_scale,
+                            double* h_S, double* h_b, double* h_cost);
+/* One damped step from the system built by the last mcba_build_reduced:
+ * Cholesky of S + lambda*D_c^2, back-substitution of every pose. d_dx: 12C + 6F. */
+int mcba_solve_step(mcba_handle* h, const double* d_x, double lambda, double* d_x_new);
+
+/* The whole Levenberg-Marquardt loop on the device (replaces the
+ * least_squares call of bundle_adjustment.py:307-313).  d_x: in x0, out solution.
+ * d_grad (12C + 6F, may be NULL) receives the gradient at the solution. */
+int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt, mcba_result* res,
+                double* d_grad);
+
+/* Gradient of 0.5*sum rho at the last evaluated point, [g_cam (12C) | g_pose (6F)] (device). */
+int mcba_gradient(mcba_handle* h, double* d_grad);
+
+/* Multi-GPU: frames are sharded across ranks; only the packed reduced system is
+ * all-reduced (NCCL).  id is the 128-byte ncclUniqueId made on rank 0. */
+int mcba_comm_unique_id(void* id128);
+int mcba_comm_init(mcba_handle* h, const void* id128, int rank, int nranks);
+
+/* geometry.py:277-325 project_points for P points and one camera:
+ * d_points (P,3), ext (6), K (3x3 row major, skew honoured), dist (k1,k2) or NULL. */
+int mcba_project_points(int device, void* cuda_stream, const double* d_points, int64_t n_points,
+                        const double* h_ext, const double* h_K, const double* h_dist,
+                        double* d_uv);
+/* bundle_adjustment.py:10-30 embed_calib_objpoints: d_poses (F,6), d_obj (N,3) -> d_world (F,N,3). */
+int mcba_embed_points(int device, void* cuda_stream, const double* d_poses, int64_t n_frames,
+                      const double* d_obj, int n_points, double* d_world);
+/* geometry.py:328-358 undistort_points (cv2.undistortPoints(uv, K, dist5, None, K): exactly
+ * five fixed-point iterations; rows with a NaN stay NaN): d_uv_in/out (P,2), h_K (3x3), h_dist (5). */
+int mcba_undistort_points(int device, void* cuda_stream, const double* d_uv_in, int64_t n_points,
+                          const double* h_K, const double* h_dist, double* d_uv_out);
+/* geometry.py:361-433 triangulate: d_uvs (C,P,2) NaN = missing, h_ext (C,6), h_K (C,3,3),
+ * h_dist (C,5); d_points (P,3). */
+int mcba_triangulate(int device, void* cuda_stream, const double* d_uvs, int n_cameras,
+                     int64_t n_points, const double* h_ext, const double* h_K,
+                     const double* h_dist, double* d_points);
+
+/* Number of kernels this handle has launched (bench.py gpu_launches). */
+int64_t mcba_kernel_launches(mcba_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCBA_H_ */

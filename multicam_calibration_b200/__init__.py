@@ -1,0 +1,17 @@
+"""B200-native bundle-adjustment engine behind the Python API of
+``multicam_calibration.bundle_adjustment`` and ``multicam_calibration.geometry``.
+
+``import multicam_calibration_b200 as mcc`` exposes the same flat namespace the
+reference builds with its star imports (``multicam_calibration/__init__.py:1-7``)
+for the two hot-path modules.
+"""
+from .geometry import (rodrigues, rodrigues_inv, rigid_transform_from_correspondences,
+                       apply_rigid_transform, get_transformation_matrix, get_transformation_vector,
+                       get_projection_matrix, euclidean_to_homogenous, homogeneous_to_euclidean,
+                       project_points, undistort_points, triangulate)
+from .bundle_adjustment import (embed_calib_objpoints, predict_calib_uvs, residuals,
+                                bundle_adjustment_sparsity, serialize_params, deserialize_params,
+                                bundle_adjust, select_frames)
+from .engine import BAProblem, OptimizeResult
+
+__version__ = "0.1.0"

@@ -1,0 +1,159 @@
+"""Drop-in for ``multicam_calibration.bundle_adjustment`` (reference
+bundle_adjustment.py:10-327) on the B200 engine.
+
+Same function names, argument order, parameter-vector layout, observation
+arrays and return values.  ``bundle_adjust`` replaces the reference's
+``scipy.optimize.least_squares(method='trf', jac_sparsity=...)`` call with a
+device Levenberg-Marquardt loop over fused residual + analytic-Jacobian +
+Schur kernels; the finite-difference sparsity pattern is never
+built on that path.
+"""
+import ctypes
+import warnings
+
+import numpy as np
+
+from . import _native
+from ._native import check
+from .engine import BAProblem
+from .geometry import project_points
+
+na = np.newaxis
+
+
+def embed_calib_objpoints(calib_objpoints, calib_poses):
+    """(N,3), (F,6) -> (F,N,3) world points (bundle_adjustment.py:10-30)."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    dev = torch.cuda.current_device()
+    obj = np.ascontiguousarray(calib_objpoints, dtype=np.float64)
+    poses = np.ascontiguousarray(calib_poses, dtype=np.float64)
+    d_obj = torch.as_tensor(obj).to(f"cuda:{dev}")
+    d_pose = torch.as_tensor(poses.reshape(-1, 6)).to(f"cuda:{dev}")
+    F, N = d_pose.shape[0], obj.shape[0]
+    d_out = torch.empty((F, N, 3), dtype=torch.float64, device=d_obj.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.mcba_embed_points(dev, stream, ctypes.c_void_p(d_pose.data_ptr()), F,
+                                ctypes.c_void_p(d_obj.data_ptr()), N, ctypes.c_void_p(d_out.data_ptr())))
+    return d_out.cpu().numpy()
+
+
+def predict_calib_uvs(all_extrinsics, all_intrinsics, calib_objpoints, calib_poses):
+    """(C,F,N,2) predicted corner positions (bundle_adjustment.py:33-63)."""
+    world = embed_calib_objpoints(calib_objpoints, calib_poses)
+    return np.stack([project_points(world, ext, *intr)
+                     for ext, intr in zip(all_extrinsics, all_intrinsics)])
+
+
+def serialize_params(all_extrinsics, all_intrinsics, calib_poses):
+    """Flat parameter vector, 12 per camera then 6 per frame (bundle_adjustment.py:128-157)."""
+    blocks = []
+    for ext, (K, dist) in zip(all_extrinsics, all_intrinsics):
+        K = np.asarray(K)
+        blocks.append(np.concatenate([[K[0, 0], K[1, 1], K[0, 2], K[1, 2]],
+                                      np.asarray(dist)[:2], np.asarray(ext)]))
+    blocks.append(np.asarray(calib_poses).ravel())
+    return np.concatenate(blocks)
+
+
+def deserialize_params(x, n_cameras):
+    """Inverse of :func:`serialize_params` (bundle_adjustment.py:160-192)."""
+    x = np.asarray(x)
+    cams = x[:12 * n_cameras].reshape(n_cameras, 12)
+    all_intrinsics = []
+    for p in cams:
+        K = np.eye(3)
+        K[[0, 1, 0, 1], [0, 1, 2, 2]] = p[:4]
+        all_intrinsics.append((K, np.pad(p[4:6], (0, 3))))
+    return np.array(cams[:, 6:]), all_intrinsics, x[12 * n_cameras:].reshape((-1, 6))
+
+
+_problems = {}
+
+
+def _problem_for(all_calib_uvs, calib_objpoints):
+    """One cached device allocation per problem shape; observations are re-uploaded
+    on every call (the caller's array may have changed)."""
+    uvs = np.asarray(all_calib_uvs)
+    key = uvs.shape
+    prob = _problems.get(key)
+    if prob is None:
+        _problems.clear()
+        prob = BAProblem(uvs, calib_objpoints)
+        _problems[key] = prob
+    else:
+        prob.set_observations(uvs, calib_objpoints)
+    return prob
+
+
+def residuals(params, all_calib_uvs, calib_objpoints):
+    """observed - predicted for every finite observation scalar, C order
+    (bundle_adjustment.py:66-98)."""
+    return _problem_for(all_calib_uvs, calib_objpoints).residuals(params)
+
+
+def bundle_adjustment_sparsity(all_calib_uvs):
+    """Jacobian sparsity pattern (bundle_adjustment.py:101-125).  Kept for API
+    parity only -- the engine uses analytic blocks and never builds it."""
+    from scipy.sparse import csr_matrix
+    C, F, N, _ = all_calib_uvs.shape
+    mask = ~np.isnan(all_calib_uvs)
+    cam = np.broadcast_to(np.arange(C)[:, na, na, na], mask.shape)[mask]
+    frm = np.broadcast_to(np.arange(F)[na, :, na, na], mask.shape)[mask]
+    cols = np.concatenate([cam[:, na] * 12 + np.arange(12), C * 12 + frm[:, na] * 6 + np.arange(6)], axis=1)
+    m = cam.size
+    A = csr_matrix((np.ones(m * 18, dtype=int), cols.ravel(), np.arange(m + 1) * 18),
+                   shape=(m, C * 12 + F * 6))
+    return A.tolil()
+
+
+def select_frames(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
+                  n_frames=10000, outlier_threshold=None):
+    """Frame eligibility, outlier rejection and sub-sampling of
+    bundle_adjustment.py:265-296 (same prints, same use of the global numpy RNG)."""
+    use_frames = np.nonzero((~np.isnan(all_calib_uvs).any((-1, -2))).sum(0) > 1)[0]
+    predicted = predict_calib_uvs(all_extrinsics, all_intrinsics, calib_objpoints, calib_poses[use_frames])
+    err = np.linalg.norm(all_calib_uvs[:, use_frames] - predicted, axis=-1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        worst_mean_err = np.nanmax(np.nanmean(err, axis=-1), axis=0)
+    if outlier_threshold is None:
+        outlier_threshold = 5 * np.nanmedian(err)
+    exclude = np.nan_to_num(worst_mean_err) > outlier_threshold
+    use_frames = use_frames[~exclude]
+    print(f"Excluding {int(exclude.sum())} out of {len(use_frames)} frames "
+          f"based on an outlier threshold of {outlier_threshold}")
+    if not (n_frames is None or n_frames > len(use_frames)):
+        use_frames = np.random.choice(use_frames, n_frames, replace=False)
+    return use_frames
+
+
+def bundle_adjust(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
+                  n_frames=10000, outlier_threshold=None, **opt_kwargs):
+    """Bundle adjustment of all cameras and board poses (bundle_adjustment.py:195-327).
+
+    Returns ``(adjusted_extrinsics, adjusted_intrinsics, adjusted_calib_poses,
+    use_frames, result)`` exactly like the reference; ``result`` has the fields of
+    ``scipy.optimize.OptimizeResult`` (``jac`` is None: the Jacobian is never
+    materialised).  ``opt_kwargs`` accepts ``ftol, xtol, gtol, max_nfev, loss
+    ('soft_l1' | 'linear'), f_scale, verbose``; when ``torch.distributed`` is
+    initialised with more than one rank the frames are sharded across ranks.
+    """
+    from . import distributed
+    all_calib_uvs = np.asarray(all_calib_uvs, dtype=np.float64)
+    calib_poses = np.asarray(calib_poses, dtype=np.float64)
+    calib_objpoints = np.asarray(calib_objpoints, dtype=np.float64)
+    n_cameras = all_calib_uvs.shape[0]
+    use_frames = select_frames(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
+                               calib_poses, n_frames, outlier_threshold)
+    x0 = serialize_params(all_extrinsics, all_intrinsics, calib_poses[use_frames])
+    if distributed.world_size() > 1:
+        x, result = distributed.solve_sharded(all_calib_uvs[:, use_frames], calib_objpoints, x0, **opt_kwargs)
+    else:
+        prob = BAProblem(all_calib_uvs[:, use_frames], calib_objpoints)
+        try:
+            x, result = prob.solve(x0, **opt_kwargs)
+        finally:
+            prob.close()
+    ext, intr, poses = deserialize_params(result.x, n_cameras)
+    return ext, intr, poses, use_frames, result

@@ -1,0 +1,385 @@
+// K1 family: camera constants, observation tiling, the materialised residual
+// vector (bundle_adjustment.py:66-98), dense predictions (:33-63), the robust
+// cost, and the per-observation analytic Jacobian blocks used by the parity tests.
+#include <cub/device/device_scan.cuh>
+
+#include "mcba_internal.h"
+#include "mcba_obs.cuh"
+
+namespace mcba {
+
+// ---------------------------------------------------------------- cameras
+__global__ void prep_cameras_kernel(const double* __restrict__ x, int C, CamConst* __restrict__ cams) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double* p = x + 12 * c;
+  CamConst k;
+  k.fx = p[0]; k.fy = p[1]; k.cx = p[2]; k.cy = p[3]; k.k1 = p[4]; k.k2 = p[5];
+  const double r[3] = {p[6], p[7], p[8]};
+  k.t[0] = p[9]; k.t[1] = p[10]; k.t[2] = p[11];
+  rodrigues(r, k.R);
+  so3_left_jacobian(r, k.Jl);
+  cross_mat3(k.t, k.Jl, k.tJ);
+  cams[c] = k;
+}
+
+int launch_prep_cameras(mcba_handle* h, const double* x) {
+  prep_cameras_kernel<<<(h->L.C + 31) / 32, 32, 0, h->stream>>>(x, h->L.C, h->d_cams);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+// ---------------------------------------------------------------- observation layouts
+// reference (C,F,N,2)  ->  tiled [tile][c][n][lane] (double2), NaN padded to 32 frames
+__global__ void tile_observations_kernel(const double2* __restrict__ ref, double2* __restrict__ tiled,
+                                         int C, long long F, int N, long long nTiles) {
+  const long long total = nTiles * C * N * kTile;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int lane = (int)(i % kTile);
+    long long r = i / kTile;
+    const int n = (int)(r % N);
+    r /= N;
+    const int c = (int)(r % C);
+    const long long tile = r / C;
+    const long long f = tile * kTile + lane;
+    double2 v = make_double2(nan(""), nan(""));
+    if (f < F) v = ref[((long long)c * F + f) * N + n];
+    tiled[i] = v;
+  }
+}
+
+// finite scalars per (c,f) row (one warp per row) + number of observed corners
+__global__ void count_rows_kernel(const double* __restrict__ ref, long long rows, int N,
+                                  long long* __restrict__ counts, unsigned long long* __restrict__ n_obs) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const double* p = ref + row * 2 * N;
+    int cnt = 0, obs = 0;
+    for (int s0 = 0; s0 < 2 * N; s0 += 32) {   // uniform trip count: the shuffle needs all lanes
+      const int s = s0 + lane;
+      const double v = s < 2 * N ? p[s] : nan("");
+      const bool fin = v == v;
+      cnt += fin;
+      const double w = __shfl_xor_sync(0xffffffffu, v, 1);  // the other scalar of the corner
+      obs += ((s & 1) == 0) && (fin || (w == w));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+      obs += __shfl_xor_sync(0xffffffffu, obs, off);
+    }
+    if (lane == 0) {
+      counts[row] = cnt;
+      if (obs) atomicAdd(n_obs, (unsigned long long)obs);
+    }
+  }
+}
+
+int launch_tile_observations(mcba_handle* h) {
+  const Layout& L = h->L;
+  const long long total = L.nTiles * L.C * L.N * kTile;
+  int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  tile_observations_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref),
+                                                       h->d_obs_tiled, L.C, L.F, L.N, L.nTiles);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+// row offsets of the NaN compaction (bundle_adjustment.py:97); only K1 needs them
+int ensure_row_offsets(mcba_handle* h) {
+  if (h->have_rows) return MCBA_OK;
+  const Layout& L = h->L;
+  int grid;
+  const long long rows = (long long)L.C * L.F;
+  unsigned long long* d_nobs = nullptr;
+  MCBA_CUDA(cudaMalloc(&d_nobs, sizeof(unsigned long long)));
+  MCBA_CUDA(cudaMemsetAsync(d_nobs, 0, sizeof(unsigned long long), h->stream));
+  MCBA_CUDA(cudaMemsetAsync(h->d_row_off, 0, sizeof(long long) * (rows + 1), h->stream));
+  grid = (int)((rows * 32 + 255) / 256 < 148 * 16 ? (rows * 32 + 255) / 256 : 148 * 16);
+  if (grid < 1) grid = 1;
+  count_rows_kernel<<<grid, 256, 0, h->stream>>>(h->d_obs_ref, rows, L.N, h->d_row_off, d_nobs);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_row_off, h->d_row_off, (int)(rows + 1), h->stream);
+  void* d_tmp = nullptr;
+  MCBA_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
+  MCBA_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, h->d_row_off, h->d_row_off, (int)(rows + 1), h->stream));
+  h->launches++;
+  long long m = 0;
+  unsigned long long nobs = 0;
+  MCBA_CUDA(cudaMemcpyAsync(&m, h->d_row_off + rows, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaMemcpyAsync(&nobs, d_nobs, sizeof(nobs), cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  MCBA_CUDA(cudaFree(d_tmp));
+  MCBA_CUDA(cudaFree(d_nobs));
+  h->m = m;
+  h->n_obs = (long long)nobs;
+  h->have_rows = true;
+  return MCBA_OK;
+}
+
+// ---------------------------------------------------------------- residual vector / predictions
+// One warp per (c,f) row of 2N scalars.  The reference's operation order is kept
+// (world point first, then camera transform: bundle_adjustment.py:27-29,
+// geometry.py:304-305) so the result agrees with it to rounding.
+template <bool kCompact>
+__global__ void residuals_kernel(const double* __restrict__ x, const double* __restrict__ ref,
+                                 const double* __restrict__ obj, const CamConst* __restrict__ cams,
+                                 const long long* __restrict__ row_off, int C, long long F, int N,
+                                 double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long rows = (long long)C * F;
+  for (long long row = warp; row < rows; row += nwarps) {
+    const int c = (int)(row / F);
+    const long long f = row % F;
+    const CamConst& cam = cams[c];
+    const double* ps = x + 12 * (long long)C + 6 * f;
+    const double rho[3] = {ps[0], ps[1], ps[2]};
+    double Rp[9];
+    rodrigues(rho, Rp);
+    long long base = kCompact ? row_off[row] : row * 2 * N;
+    for (int s0 = 0; s0 < 2 * N; s0 += 32) {
+      const int s = s0 + lane;
+      bool fin = false;
+      double val = 0.0;
+      if (s < 2 * N) {
+        const int n = s >> 1;
+        const double q[3] = {obj[3 * n], obj[3 * n + 1], obj[3 * n + 2]};
+        double Xw[3], Xc[3];
+        mat3_vec(Rp, q, Xw);
+        Xw[0] += ps[3]; Xw[1] += ps[4]; Xw[2] += ps[5];
+        mat3_vec(cam.R, Xw, Xc);
+        Xc[0] += cam.t[0]; Xc[1] += cam.t[1]; Xc[2] += cam.t[2];
+        const double xn = Xc[0] / Xc[2], yn = Xc[1] / Xc[2];
+        const double r2 = xn * xn + yn * yn;
+        const double d = 1.0 + cam.k1 * r2 + cam.k2 * (r2 * r2);
+        const double pred = (s & 1) ? (cam.fy * (Xc[1] * d) + cam.cy * Xc[2]) / Xc[2]
+                                    : (cam.fx * (Xc[0] * d) + cam.cx * Xc[2]) / Xc[2];
+        if (kCompact) {
+          const double o = ref[row * 2 * N + s];
+          fin = o == o;
+          val = o - pred;
+        } else {
+          val = pred;
+        }
+      }
+      if (kCompact) {
+        const unsigned mask = __ballot_sync(0xffffffffu, fin);
+        if (fin) out[base + __popc(mask & ((1u << lane) - 1))] = val;
+        base += __popc(mask);
+      } else if (s < 2 * N) {
+        out[base + s] = val;
+      }
+    }
+  }
+}
+
+static int rows_grid(long long rows) {
+  long long g = (rows * 32 + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int launch_residuals(mcba_handle* h, const double* x, double* r_out) {
+  const Layout& L = h->L;
+  int rc = launch_prep_cameras(h, x);
+  if (rc) return rc;
+  residuals_kernel<true><<<rows_grid((long long)L.C * L.F), 256, 0, h->stream>>>(
+      x, h->d_obs_ref, h->d_obj, h->d_cams, h->d_row_off, L.C, L.F, L.N, r_out);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+int launch_predict(mcba_handle* h, const double* x, double* uv_out) {
+  const Layout& L = h->L;
+  int rc = launch_prep_cameras(h, x);
+  if (rc) return rc;
+  residuals_kernel<false><<<rows_grid((long long)L.C * L.F), 256, 0, h->stream>>>(
+      x, nullptr, h->d_obj, h->d_cams, nullptr, L.C, L.F, L.N, uv_out);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+// ---------------------------------------------------------------- robust cost
+// warp per (tile, camera), lane = frame, tiled SoA (same stream as K2a without the Jacobian)
+__global__ void __launch_bounds__(256) cost_kernel(const double* __restrict__ x, const double2* __restrict__ obs,
+                                                   const double* __restrict__ obj, const CamConst* __restrict__ cams,
+                                                   int C, long long F, int N, long long nTiles, int loss, double inv_c,
+                                                   double c2, double* __restrict__ part, unsigned int* __restrict__ counter,
+                                                   double* __restrict__ out) {
+  extern __shared__ double s_obj[];
+  __shared__ double s_red[8 * 3];
+  __shared__ bool s_last;
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_obj[i] = obj[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = blockIdx.x * (long long)(blockDim.x >> 5) + warp;
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  double cost = 0.0, sumsq = 0.0, cnt = 0.0;
+  for (long long job = gw; job < nTiles * C; job += nw) {
+    const long long tile = job / C;
+    const int c = (int)(job % C);
+    const long long f = tile * kTile + lane;
+    if (f < F) {
+      const CamConst& cam = cams[c];
+      const Intr in{cam.fx, cam.fy, cam.cx, cam.cy, cam.k1, cam.k2};
+      const double* ps = x + 12 * (long long)C + 6 * f;
+      const double rho[3] = {ps[0], ps[1], ps[2]}, tau[3] = {ps[3], ps[4], ps[5]};
+      double Rp[9], Rcf[9], tcf[3];
+      rodrigues(rho, Rp);
+      mat3_mul(cam.R, Rp, Rcf);
+      mat3_vec(cam.R, tau, tcf);
+      tcf[0] += cam.t[0]; tcf[1] += cam.t[1]; tcf[2] += cam.t[2];
+      const double2* ob = obs + (size_t)job * N * kTile + lane;
+#pragma unroll 5
+      for (int n = 0; n < N; ++n) {
+        const double2 o = ob[(size_t)n * kTile];
+        const bool hu = o.x == o.x, hv = o.y == o.y;
+        if (hu | hv) {
+          double pu, pv;
+          project(in, Rcf, tcf, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], pu, pv);
+          double rho_, wg, wh;
+          if (hu) {
+            const double fu = o.x - pu;
+            robust_weights(loss, fu, inv_c, c2, rho_, wg, wh);
+            cost += rho_; sumsq += fu * fu; cnt += 1.0;
+          }
+          if (hv) {
+            const double fv = o.y - pv;
+            robust_weights(loss, fv, inv_c, c2, rho_, wg, wh);
+            cost += rho_; sumsq += fv * fv; cnt += 1.0;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    cost += __shfl_xor_sync(0xffffffffu, cost, off);
+    sumsq += __shfl_xor_sync(0xffffffffu, sumsq, off);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  if (lane == 0) { s_red[warp * 3] = cost; s_red[warp * 3 + 1] = sumsq; s_red[warp * 3 + 2] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, k = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_red[w * 3]; b += s_red[w * 3 + 1]; k += s_red[w * 3 + 2]; }
+    part[blockIdx.x * 3] = 0.5 * a;
+    part[blockIdx.x * 3 + 1] = b;
+    part[blockIdx.x * 3 + 2] = k;
+    __threadfence();
+    s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {   // deterministic final sum by the last CTA to finish
+    __threadfence();
+    double a = 0, b = 0, k = 0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a += __ldcg(part + i * 3); b += __ldcg(part + i * 3 + 1); k += __ldcg(part + i * 3 + 2);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      b += __shfl_xor_sync(0xffffffffu, b, off);
+      k += __shfl_xor_sync(0xffffffffu, k, off);
+    }
+    __syncthreads();
+    if (lane == 0) { s_red[warp * 3] = a; s_red[warp * 3 + 1] = b; s_red[warp * 3 + 2] = k; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      a = b = k = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_red[w * 3]; b += s_red[w * 3 + 1]; k += s_red[w * 3 + 2]; }
+      out[0] = a; out[1] = b; out[2] = k;
+      *counter = 0;
+    }
+  }
+}
+
+int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, double* out_scal) {
+  const Layout& L = h->L;
+  int rc = launch_prep_cameras(h, x);
+  if (rc) return rc;
+  double* part = h->d_scal + 64;                                  // [grid_cost][3]
+  unsigned int* counter = reinterpret_cast<unsigned int*>(h->d_scal + 32);
+  cost_kernel<<<h->grid_cost, 256, sizeof(double) * 3 * L.N, h->stream>>>(
+      x, h->d_obs_tiled, h->d_obj, h->d_cams, L.C, L.F, L.N, L.nTiles, loss, 1.0 / f_scale,
+      f_scale * f_scale, part, counter, out_scal);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+// ---------------------------------------------------------------- Jacobian blocks (parity path)
+// One thread per (c,f,n).  RESIDUAL Jacobian = -(prediction Jacobian).
+__global__ void jacobian_blocks_kernel(const double* __restrict__ x, const double* __restrict__ obj,
+                                       const CamConst* __restrict__ cams, int C, long long F, int N,
+                                       double* __restrict__ Jc, double* __restrict__ Jp) {
+  const long long total = (long long)C * F * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const long long f = (i / N) % F;
+    const int c = (int)(i / ((long long)N * F));
+    const CamConst& cam = cams[c];
+    const Intr in{cam.fx, cam.fy, cam.cx, cam.cy, cam.k1, cam.k2};
+    const double* ps = x + 12 * (long long)C + 6 * f;
+    const double rho[3] = {ps[0], ps[1], ps[2]}, tau[3] = {ps[3], ps[4], ps[5]};
+    double Rp[9], Jlp[9], Rcf[9], tcf[3], K[9], RJ[9], KJ[9];
+    rodrigues(rho, Rp);
+    so3_left_jacobian(rho, Jlp);
+    mat3_mul(cam.R, Rp, Rcf);
+    mat3_vec(cam.R, tau, tcf);
+    tcf[0] += cam.t[0]; tcf[1] += cam.t[1]; tcf[2] += cam.t[2];
+    cross_mat3(tcf, cam.R, K);
+    mat3_mul(cam.R, Jlp, RJ);   // R_c J_l(rho)
+    mat3_mul(K, Jlp, KJ);       // [t_cf]x R_c J_l(rho)
+    double pu, pv, a[2][10];
+    project_jac(in, Rcf, tcf, obj[3 * n], obj[3 * n + 1], obj[3 * n + 2], pu, pv, a[0], a[1]);
+    for (int row = 0; row < 2; ++row) {
+      const double* ar = a[row];
+      double* jc = Jc + (i * 2 + row) * 12;
+      double* jp = Jp + (i * 2 + row) * 6;
+      for (int k = 0; k < 12; ++k) jc[k] = 0.0;
+      jc[row] = -ar[0];            // fx | fy
+      jc[2 + row] = -ar[1];        // cx | cy
+      jc[4] = -ar[2];
+      jc[5] = -ar[3];
+      const double* m = ar + 4;
+      const double* G = ar + 7;
+      for (int k = 0; k < 3; ++k) {
+        jc[6 + k] = -(m[0] * cam.Jl[k] + m[1] * cam.Jl[3 + k] + m[2] * cam.Jl[6 + k] +
+                      G[0] * cam.tJ[k] + G[1] * cam.tJ[3 + k] + G[2] * cam.tJ[6 + k]);
+        jc[9 + k] = -G[k];
+        jp[k] = -(m[0] * RJ[k] + m[1] * RJ[3 + k] + m[2] * RJ[6 + k] +
+                  G[0] * KJ[k] + G[1] * KJ[3 + k] + G[2] * KJ[6 + k]);
+        jp[3 + k] = -(G[0] * cam.R[k] + G[1] * cam.R[3 + k] + G[2] * cam.R[6 + k]);
+      }
+    }
+  }
+}
+
+int launch_jacobian_blocks(mcba_handle* h, const double* x, double* Jc, double* Jp) {
+  const Layout& L = h->L;
+  int rc = launch_prep_cameras(h, x);
+  if (rc) return rc;
+  const long long total = (long long)L.C * L.F * L.N;
+  long long g = (total + 127) / 128;
+  if (g > 148 * 8) g = 148 * 8;
+  jacobian_blocks_kernel<<<(int)g, 128, 0, h->stream>>>(x, h->d_obj, h->d_cams, L.C, L.F, L.N, Jc, Jp);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+}  // namespace mcba

@@ -1,0 +1,496 @@
+// C-ABI entry points of libmcba (see include/mcba.h), the handle life cycle and
+// the Levenberg-Marquardt driver that replaces scipy.optimize.least_squares for
+// bundle_adjustment.py:307-313.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "mcba_internal.h"
+
+namespace mcba {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+int solve_reduced(mcba_handle* h, double lambda);
+
+// ------------------------------------------------------------------ NCCL (resolved lazily: torch already maps libnccl.so.2)
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return MCBA_OK;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) {
+    set_error(std::string("cannot load libnccl: ") + dlerror());
+    return MCBA_ERR_NCCL;
+  }
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    set_error("libnccl is missing required symbols");
+    return MCBA_ERR_NCCL;
+  }
+  g_nccl.lib = lib;
+  return MCBA_OK;
+}
+
+int allreduce_packed(mcba_handle* h, double* buf, long long n) {
+  if (h->nranks <= 1 || !h->nccl_comm) return MCBA_OK;
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream);
+  if (r != ncclSuccess) {
+    set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    return MCBA_ERR_NCCL;
+  }
+  h->launches++;
+  return MCBA_OK;
+}
+
+// ------------------------------------------------------------------ evaluation helpers
+struct EvalOut {
+  double cost, sumsq, count, gnorm;
+};
+
+// residual + Jacobian + Schur at x; the packed system is left (all-reduced) in d_red
+static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, double f_scale) {
+  int rc;
+  if ((rc = launch_prep_cameras(h, x))) return rc;
+  if ((rc = launch_k2_frames(h, x, lambda, loss, f_scale))) return rc;
+  if ((rc = launch_k2_syrk(h))) return rc;
+  if ((rc = launch_finalize(h))) return rc;
+  if ((rc = allreduce_packed(h, h->d_red, h->L.redLen))) return rc;
+  return MCBA_OK;
+}
+
+static int read_eval(mcba_handle* h, EvalOut* out) {
+  const Layout& L = h->L;
+  const long long tail = L.redLen - L.offB;
+  MCBA_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_red + L.offB, sizeof(double) * tail, cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  const double* t = h->h_pinned;
+  const double* g = t + (L.offG - L.offB);
+  const double* sc = t + (L.offScal - L.offB);
+  const double* rk = t + (L.offRank - L.offB);
+  double gn = 0.0;
+  for (int i = 0; i < L.nc; ++i) gn = std::max(gn, std::fabs(g[i]));
+  bool bad = false;
+  for (int i = 0; i < L.nc; ++i) bad |= !std::isfinite(g[i]);
+  for (int i = 0; i < kMaxRanks; ++i) gn = std::max(gn, rk[i]);
+  out->cost = sc[kRsCost];
+  out->sumsq = sc[kRsSumSq];
+  out->count = sc[kRsCount];
+  out->gnorm = bad ? NAN : gn;
+  return MCBA_OK;
+}
+
+}  // namespace mcba
+
+using namespace mcba;
+
+extern "C" {
+
+const char* mcba_last_error(void) { return g_error.c_str(); }
+int mcba_version(void) { return 100; }
+
+void mcba_default_options(mcba_options* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->ftol = 1e-4;  // bundle_adjustment.py:302
+  o->xtol = 1e-8;
+  o->gtol = 1e-8;
+  o->max_nfev = 0;
+  o->loss = MCBA_LOSS_SOFT_L1;
+  o->f_scale = 1.0;
+  o->verbose = 2;
+  o->lambda0 = 1e-3;
+  o->lambda_min = 1e-12;
+  o->lambda_max = 1e12;
+}
+
+int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
+  if (!out || C < 1 || F < 1 || N < 1) {
+    set_error("mcba_create: n_cameras, n_frames, n_points must be >= 1");
+    return MCBA_ERR_ARG;
+  }
+  if (C > 32) {
+    set_error("mcba_create: at most 32 cameras are supported");
+    return MCBA_ERR_ARG;
+  }
+  MCBA_CUDA(cudaSetDevice(device));
+  mcba_handle* h = new mcba_handle();
+  h->device = device;
+  Layout& L = h->L;
+  L.C = C; L.N = N; L.F = F;
+  L.nTiles = (F + kTile - 1) / kTile;
+  L.Fpad = L.nTiles * kTile;
+  L.nc = 12 * C;
+  L.offS = 0;
+  L.offB = (long long)L.nc * L.nc;
+  L.offG = L.offB + L.nc;
+  L.offDiag = L.offG + L.nc;
+  L.offScal = L.offDiag + L.nc;
+  L.offRank = L.offScal + kRsNum;
+  L.redLen = L.offRank + kMaxRanks;
+  cudaDeviceProp prop;
+  MCBA_CUDA(cudaGetDeviceProperties(&prop, device));
+  h->n_sm = prop.multiProcessorCount;
+  MCBA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->grid_frames = (int)std::min<long long>(L.nTiles, h->n_sm);
+  const int FB = L.nc <= 96 ? 32 : (L.nc <= 192 ? 12 : 4);
+  h->grid_syrk = (int)std::min<long long>((F + FB - 1) / FB, 2LL * h->n_sm);
+  h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
+  h->grid_back = (int)std::min<long long>(L.nTiles, 8LL * h->n_sm);
+  const long long n = L.nc + 6 * F;
+  const int nb = L.nc / 6, nT = nb * (nb + 1) / 2;
+  auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8); };
+#define MCBA_ALLOC(ptr, count) MCBA_CUDA(alloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
+  MCBA_ALLOC(h->d_obs_ref, (size_t)C * F * N * 2);
+  MCBA_ALLOC(h->d_obs_tiled, (size_t)L.nTiles * C * N * kTile);
+  MCBA_ALLOC(h->d_obj, 3 * N);
+  MCBA_ALLOC(h->d_row_off, (size_t)C * F + 1);
+  MCBA_ALLOC(h->d_x, n);
+  MCBA_ALLOC(h->d_xtrial, n);
+  MCBA_ALLOC(h->d_cams, C);
+  MCBA_ALLOC(h->d_Z, (size_t)L.Fpad * 6 * L.nc);
+  MCBA_ALLOC(h->d_Linv, (size_t)L.nTiles * 21 * kTile);
+  MCBA_ALLOC(h->d_y, (size_t)L.nTiles * 6 * kTile);
+  MCBA_ALLOC(h->d_gpose, (size_t)L.Fpad * 6);
+  MCBA_ALLOC(h->d_D2pose, (size_t)L.nTiles * 6 * kTile);
+  MCBA_ALLOC(h->d_D2cam, L.nc);
+  MCBA_ALLOC(h->d_partU, (size_t)h->grid_frames * C * kUPad);
+  MCBA_ALLOC(h->d_partS, (size_t)h->grid_frames * kRsNum);
+  MCBA_ALLOC(h->d_partSyrk, (size_t)h->grid_syrk * ((size_t)nT * 36 + (size_t)nb * 6));
+  MCBA_ALLOC(h->d_red, L.redLen);
+  MCBA_ALLOC(h->d_Sd, (size_t)L.nc * L.nc);
+  MCBA_ALLOC(h->d_dcam, 2 * L.nc);
+  MCBA_ALLOC(h->d_scal, 64 + 7 * 4096);
+  MCBA_ALLOC(h->d_info, 4);
+  MCBA_CUDA(cudaMemset(h->d_D2pose, 0, sizeof(double) * L.nTiles * 6 * kTile));
+  MCBA_CUDA(cudaMemset(h->d_D2cam, 0, sizeof(double) * L.nc));
+  MCBA_CUDA(cudaMemset(h->d_scal, 0, sizeof(double) * (64 + 7 * 4096)));
+  MCBA_CUDA(cudaMemset(h->d_info, 0, sizeof(int) * 4));
+  MCBA_CUDA(cudaMemset(h->d_gpose, 0, sizeof(double) * L.Fpad * 6));
+  MCBA_CUDA(cudaMallocHost((void**)&h->h_pinned, sizeof(double) * (L.redLen + 64)));
+  if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnCreate failed");
+    return MCBA_ERR_SOLVER;
+  }
+  cusolverDnSetStream(h->solver, h->stream);
+  if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, L.nc, h->d_Sd, L.nc, &h->lwork) != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnDpotrf_bufferSize failed");
+    return MCBA_ERR_SOLVER;
+  }
+  MCBA_ALLOC(h->d_work, h->lwork);
+  *out = h;
+  return MCBA_OK;
+}
+
+int mcba_destroy(mcba_handle* h) {
+  if (!h) return MCBA_OK;
+  cudaSetDevice(h->device);
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
+  if (h->solver) cusolverDnDestroy(h->solver);
+  void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
+                  h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MCBA_OK;
+}
+
+int mcba_set_stream(mcba_handle* h, void* s) {
+  if (!h) return MCBA_ERR_ARG;
+  MCBA_CUDA(cudaSetDevice(h->device));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (s) {
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)s;
+    h->own_stream = false;
+  } else if (!h->own_stream) {
+    MCBA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  cusolverDnSetStream(h->solver, h->stream);
+  return MCBA_OK;
+}
+
+int mcba_synchronize(mcba_handle* h) {
+  MCBA_CUDA(cudaSetDevice(h->device));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  return MCBA_OK;
+}
+
+int mcba_set_observations(mcba_handle* h, const double* uvs, const double* obj, int is_device) {
+  if (!h || !uvs || !obj) { set_error("mcba_set_observations: null argument"); return MCBA_ERR_ARG; }
+  MCBA_CUDA(cudaSetDevice(h->device));
+  const Layout& L = h->L;
+  const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  MCBA_CUDA(cudaMemcpyAsync(h->d_obs_ref, uvs, sizeof(double) * (size_t)L.C * L.F * L.N * 2, kind, h->stream));
+  MCBA_CUDA(cudaMemcpyAsync(h->d_obj, obj, sizeof(double) * 3 * L.N, kind, h->stream));
+  int rc = launch_tile_observations(h);
+  if (rc) return rc;
+  h->have_obs = true;
+  h->have_rows = false;
+  // a new problem: reset the running Marquardt scaling
+  MCBA_CUDA(cudaMemsetAsync(h->d_D2pose, 0, sizeof(double) * L.nTiles * 6 * kTile, h->stream));
+  MCBA_CUDA(cudaMemsetAsync(h->d_D2cam, 0, sizeof(double) * L.nc, h->stream));
+  return MCBA_OK;
+}
+
+static int need_obs(mcba_handle* h) {
+  if (!h || !h->have_obs) { set_error("observations not set (call mcba_set_observations first)"); return MCBA_ERR_STATE; }
+  MCBA_CUDA(cudaSetDevice(h->device));
+  return MCBA_OK;
+}
+
+int mcba_num_residuals(mcba_handle* h, int64_t* m, int64_t* nobs) {
+  int rc = need_obs(h);
+  if (rc) return rc;
+  if ((rc = ensure_row_offsets(h))) return rc;
+  if (m) *m = h->m;
+  if (nobs) *nobs = h->n_obs;
+  return MCBA_OK;
+}
+
+int mcba_residuals(mcba_handle* h, const double* d_x, double* d_r) {
+  int rc = need_obs(h);
+  if (rc) return rc;
+  if ((rc = ensure_row_offsets(h))) return rc;
+  return launch_residuals(h, d_x, d_r);
+}
+
+int mcba_predict(mcba_handle* h, const double* d_x, double* d_uv) {
+  if (!h) return MCBA_ERR_ARG;
+  MCBA_CUDA(cudaSetDevice(h->device));
+  return launch_predict(h, d_x, d_uv);
+}
+
+int mcba_jacobian_blocks(mcba_handle* h, const double* d_x, double* d_Jc, double* d_Jp) {
+  if (!h) return MCBA_ERR_ARG;
+  MCBA_CUDA(cudaSetDevice(h->device));
+  return launch_jacobian_blocks(h, d_x, d_Jc, d_Jp);
+}
+
+int mcba_cost(mcba_handle* h, const double* d_x, int loss, double f_scale, double* cost, double* sumsq, int64_t* count) {
+  int rc = need_obs(h);
+  if (rc) return rc;
+  if ((rc = launch_cost(h, d_x, loss, f_scale, h->d_scal))) return rc;
+  if ((rc = allreduce_packed(h, h->d_scal, 3))) return rc;
+  MCBA_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_scal, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (cost) *cost = h->h_pinned[0];
+  if (sumsq) *sumsq = h->h_pinned[1];
+  if (count) *count = (int64_t)h->h_pinned[2];
+  return MCBA_OK;
+}
+
+int mcba_build_reduced(mcba_handle* h, const double* d_x, double lambda, int loss, double f_scale, double* h_S,
+                       double* h_b, double* h_gcam, double* h_cost) {
+  int rc = need_obs(h);
+  if (rc) return rc;
+  if ((rc = evaluate(h, d_x, lambda, loss, f_scale))) return rc;
+  const Layout& L = h->L;
+  if (h_S) MCBA_CUDA(cudaMemcpyAsync(h_S, h->d_red + L.offS, sizeof(double) * L.nc * L.nc, cudaMemcpyDeviceToHost, h->stream));
+  if (h_b) MCBA_CUDA(cudaMemcpyAsync(h_b, h->d_red + L.offB, sizeof(double) * L.nc, cudaMemcpyDeviceToHost, h->stream));
+  if (h_gcam) MCBA_CUDA(cudaMemcpyAsync(h_gcam, h->d_red + L.offG, sizeof(double) * L.nc, cudaMemcpyDeviceToHost, h->stream));
+  if (h_cost) MCBA_CUDA(cudaMemcpyAsync(h_cost, h->d_red + L.offScal + kRsCost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  return MCBA_OK;
+}
+
+int mcba_build_reduced_host(mcba_handle* h, const double* h_uvs, const double* h_obj, const double* h_x,
+                            double lambda, int loss, double f_scale, double* h_S, double* h_b, double* h_cost) {
+  if (!h) return MCBA_ERR_ARG;
+  int rc = mcba_set_observations(h, h_uvs, h_obj, 0);
+  if (rc) return rc;
+  const long long n = h->L.nc + 6 * h->L.F;
+  MCBA_CUDA(cudaMemcpyAsync(h->d_x, h_x, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  return mcba_build_reduced(h, h->d_x, lambda, loss, f_scale, h_S, h_b, nullptr, h_cost);
+}
+
+int mcba_solve_step(mcba_handle* h, const double* d_x, double lambda, double* d_x_new) {
+  int rc = need_obs(h);
+  if (rc) return rc;
+  if ((rc = solve_reduced(h, lambda))) return rc;
+  if ((rc = launch_backsub(h, d_x, d_x_new, lambda))) return rc;
+  int info[2] = {0, 0};
+  MCBA_CUDA(cudaMemcpyAsync(info, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (info[0] != 0) { set_error("reduced camera system is not positive definite (potrf info = " + std::to_string(info[0]) + ")"); return MCBA_ERR_SOLVER; }
+  return MCBA_OK;
+}
+
+int mcba_gradient(mcba_handle* h, double* d_grad) {
+  // gradient of 0.5 sum rho at the last evaluated point: [g_cam | g_pose]
+  const Layout& L = h->L;
+  MCBA_CUDA(cudaMemcpyAsync(d_grad, h->d_red + L.offG, sizeof(double) * L.nc, cudaMemcpyDeviceToDevice, h->stream));
+  MCBA_CUDA(cudaMemcpyAsync(d_grad + L.nc, h->d_gpose, sizeof(double) * 6 * L.F, cudaMemcpyDeviceToDevice, h->stream));
+  return MCBA_OK;
+}
+
+int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_result* res, double* d_grad) {
+  int rc = need_obs(h);
+  if (rc) return rc;
+  if (!d_x || !res) { set_error("mcba_lm_run: null argument"); return MCBA_ERR_ARG; }
+  mcba_options opt;
+  if (opt_in) opt = *opt_in; else mcba_default_options(&opt);
+  const Layout& L = h->L;
+  const long long n_local = L.nc + 6 * L.F;
+  if (opt.lambda0 <= 0) opt.lambda0 = 1e-3;
+  if (opt.lambda_min <= 0) opt.lambda_min = 1e-12;
+  if (opt.lambda_max <= 0) opt.lambda_max = 1e12;
+  if (opt.f_scale <= 0) { set_error("f_scale must be positive"); return MCBA_ERR_ARG; }
+  std::memset(res, 0, sizeof(*res));
+  const long long launches0 = h->launches;
+
+  cudaEvent_t ev0, ev1;
+  MCBA_CUDA(cudaEventCreate(&ev0));
+  MCBA_CUDA(cudaEventCreate(&ev1));
+  MCBA_CUDA(cudaEventRecord(ev0, h->stream));
+
+  double* x = h->d_x;
+  double* xt = h->d_xtrial;
+  MCBA_CUDA(cudaMemcpyAsync(x, d_x, sizeof(double) * n_local, cudaMemcpyDeviceToDevice, h->stream));
+  // fresh Marquardt scaling for this solve
+  MCBA_CUDA(cudaMemsetAsync(h->d_D2pose, 0, sizeof(double) * L.nTiles * 6 * kTile, h->stream));
+  MCBA_CUDA(cudaMemsetAsync(h->d_D2cam, 0, sizeof(double) * L.nc, h->stream));
+
+  double lambda = opt.lambda0, nu = 2.0;
+  EvalOut ev;
+  if ((rc = evaluate(h, x, lambda, opt.loss, opt.f_scale))) return rc;
+  if ((rc = read_eval(h, &ev))) return rc;
+  int nfev = 1, njev = 1, iter = 0, status = -2;
+  if (!std::isfinite(ev.cost) || !std::isfinite(ev.gnorm)) {
+    set_error("Residuals are not finite in the initial point.");
+    return MCBA_ERR_NONFINITE;
+  }
+  // total parameter count across ranks decides the default evaluation budget (scipy: 100 n)
+  long long n_total = n_local;
+  int max_nfev = opt.max_nfev > 0 ? opt.max_nfev : (int)std::min<long long>(100 * n_total, 2000000000LL);
+  double cost = ev.cost;
+  res->cost0 = cost;
+  double step_norm = 0.0;
+  if (opt.iter_callback) opt.iter_callback(opt.callback_user, 0, nfev, cost, NAN, NAN, ev.gnorm);
+  if (ev.gnorm < opt.gtol) status = 1;
+
+  while (status == -2) {
+    if (nfev >= max_nfev) { status = 0; break; }
+    if ((rc = solve_reduced(h, lambda))) return rc;
+    if ((rc = launch_backsub(h, x, xt, lambda))) return rc;
+    if ((rc = launch_cost(h, xt, opt.loss, opt.f_scale, h->d_scal))) return rc;
+    if ((rc = allreduce_packed(h, h->d_scal, 12))) return rc;
+    MCBA_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_scal, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
+    MCBA_CUDA(cudaMemcpyAsync(h->h_pinned + 16, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    MCBA_CUDA(cudaStreamSynchronize(h->stream));
+    ++nfev;
+    const double cost_new = h->h_pinned[0];
+    const double dd = h->h_pinned[8], xx = h->h_pinned[9], gd = h->h_pinned[10], dDd = h->h_pinned[11];
+    const int info = reinterpret_cast<const int*>(h->h_pinned + 16)[0];
+    const bool solve_ok = info == 0 && std::isfinite(cost_new) && std::isfinite(dd);
+    const double pred = -0.5 * gd + 0.5 * lambda * dDd;
+    const double actual = cost - cost_new;
+    const double ratio = (solve_ok && pred > 0) ? actual / pred : -1.0;
+    const double sn = std::sqrt(dd), xn = std::sqrt(xx);
+    bool accepted = solve_ok && actual > 0;
+    int term = -2;
+    if (solve_ok) {
+      const bool f_ok = actual < opt.ftol * cost && ratio > 0.25;   // scipy common.py:705-717
+      const bool x_ok = sn < opt.xtol * (opt.xtol + xn);
+      if (f_ok && x_ok) term = 4; else if (f_ok) term = 2; else if (x_ok) term = 3;
+    }
+    if (accepted) {
+      std::swap(x, xt);
+      step_norm = sn;
+      const double t = 2.0 * ratio - 1.0;
+      lambda = std::max(opt.lambda_min, lambda * std::max(1.0 / 3.0, 1.0 - t * t * t));
+      nu = 2.0;
+      ++iter;
+      if ((rc = evaluate(h, x, lambda, opt.loss, opt.f_scale))) return rc;
+      if ((rc = read_eval(h, &ev))) return rc;
+      ++njev;
+      const double cost_prev = cost;
+      cost = ev.cost;
+      if (opt.iter_callback) opt.iter_callback(opt.callback_user, iter, nfev, cost, cost_prev - cost, sn, ev.gnorm);
+      if (term != -2) status = term;
+      else if (ev.gnorm < opt.gtol) status = 1;
+    } else {
+      if (term == 3 || term == 4) { status = 3; break; }   // step too small to matter (xtol)
+      lambda *= nu;
+      nu *= 2.0;
+      if (lambda > opt.lambda_max) { status = -1; set_error("damping exceeded lambda_max without finding a descent step"); break; }
+      if ((rc = evaluate(h, x, lambda, opt.loss, opt.f_scale))) return rc;   // pose damping is baked into Z
+      if ((rc = read_eval(h, &ev))) return rc;
+    }
+  }
+
+  MCBA_CUDA(cudaMemcpyAsync(d_x, x, sizeof(double) * n_local, cudaMemcpyDeviceToDevice, h->stream));
+  if (d_grad) { if ((rc = mcba_gradient(h, d_grad))) return rc; }
+  MCBA_CUDA(cudaEventRecord(ev1, h->stream));
+  MCBA_CUDA(cudaEventSynchronize(ev1));
+  float ms = 0;
+  MCBA_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  res->cost = cost;
+  res->optimality = ev.gnorm;
+  res->rms = ev.count > 0 ? std::sqrt(ev.sumsq / ev.count) : 0.0;
+  res->step_norm = step_norm;
+  res->lambda = lambda;
+  res->solve_ms = ms;
+  res->n_residuals = (int64_t)ev.count;
+  res->nfev = nfev;
+  res->njev = njev;
+  res->iterations = iter;
+  res->status = status;
+  res->kernel_launches = h->launches - launches0;
+  return MCBA_OK;
+}
+
+int mcba_comm_unique_id(void* id128) {
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) { set_error("ncclGetUniqueId failed"); return MCBA_ERR_NCCL; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id128, &id, 128);
+  return MCBA_OK;
+}
+
+int mcba_comm_init(mcba_handle* h, const void* id128, int rank, int nranks) {
+  if (!h || !id128 || rank < 0 || rank >= nranks || nranks > kMaxRanks) { set_error("mcba_comm_init: bad arguments"); return MCBA_ERR_ARG; }
+  int rc = load_nccl();
+  if (rc) return rc;
+  MCBA_CUDA(cudaSetDevice(h->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  ncclComm_t comm;
+  ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    return MCBA_ERR_NCCL;
+  }
+  h->nccl_comm = comm;
+  h->rank = rank;
+  h->nranks = nranks;
+  return MCBA_OK;
+}
+
+int64_t mcba_kernel_launches(mcba_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Internal (non-ABI) declarations shared by the translation units of libmcba.
+#pragma once
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/mcba.h"
+#include "mcba_math.cuh"
+
+namespace mcba {
+
+// Scalars that travel with the reduced camera system (appended to the packed
+// buffer so that ONE all-reduce per evaluation carries everything).
+enum RedScalar : int {
+  kRsCost = 0,      // 0.5 * sum rho
+  kRsSumSq = 1,     // sum f^2 (for the reprojection RMS)
+  kRsCount = 2,     // number of finite scalar residuals
+  kRsGmaxPose = 3,  // max |g| over this rank's pose gradients (NOT summed: slot per rank below)
+  kRsNum = 8
+};
+
+constexpr int kMaxRanks = 64;
+constexpr int kUPad = 96;  // 78 (A upper triangle) + 12 (q) padded to 3 x 32
+
+struct Layout {
+  int C = 0, N = 0;
+  long long F = 0, nTiles = 0, Fpad = 0;
+  int nc = 0;  // 12 C
+  // packed reduced buffer offsets (doubles)
+  long long offS = 0, offB = 0, offG = 0, offDiag = 0, offScal = 0, offRank = 0, redLen = 0;
+};
+
+struct K2Params {
+  int C, N, nwarps, ngroups;
+  long long F, nTiles;
+  const double2* obs;  // tiled [tile][c][n][lane]
+  const double* obj;   // (N,3)
+  const double* x;     // 12C + 6F
+  const CamConst* cams;
+  double lambda;
+  int loss;
+  double inv_c, c2;
+  double* Z;       // [f][k][12C]
+  double* Linv;    // [tile][21][32]
+  double* y;       // [tile][6][32]
+  double* gpose;   // [f][6]
+  double* D2pose;  // [tile][6][32] running max of diag(V_f)
+  double* partU;   // [grid][C][kUPad]
+  double* partS;   // [grid][kRsNum]
+};
+
+}  // namespace mcba
+
+struct mcba_handle {
+  mcba::Layout L;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int n_sm = 148;
+  // observations
+  double* d_obs_ref = nullptr;   // (C,F,N,2) reference layout
+  double2* d_obs_tiled = nullptr;
+  double* d_obj = nullptr;
+  long long* d_row_off = nullptr;  // (C*F + 1) exclusive scan of finite scalars per (c,f)
+  long long m = 0;                 // finite scalar residuals
+  long long n_obs = 0;             // (c,f,n) with at least one finite scalar
+  bool have_obs = false;
+  bool have_rows = false;          // row offsets / m / n_obs computed (lazily, K1 only)
+  // state
+  double* d_x = nullptr;
+  double* d_xtrial = nullptr;
+  mcba::CamConst* d_cams = nullptr;
+  double* d_Z = nullptr;
+  double* d_Linv = nullptr;
+  double* d_y = nullptr;
+  double* d_gpose = nullptr;
+  double* d_D2pose = nullptr;
+  double* d_D2cam = nullptr;  // running max of diag(U) (true basis), 12C
+  double* d_partU = nullptr;
+  double* d_partS = nullptr;
+  double* d_partSyrk = nullptr;
+  double* d_Sraw = nullptr;   // 12C x 12C raw-basis sum Z Z^T  | b part
+  double* d_red = nullptr;    // packed reduced system (see Layout)
+  double* d_Sd = nullptr;     // damped copy handed to potrf
+  double* d_dcam = nullptr;   // [delta_cam true (12C) | delta_cam raw (12C)]
+  double* d_scal = nullptr;   // step scalars (device), partials
+  double* h_pinned = nullptr; // pinned host mirror for small read-backs
+  int grid_frames = 0, grid_syrk = 0, grid_cost = 0, grid_back = 0;
+  // solver
+  cusolverDnHandle_t solver = nullptr;
+  double* d_work = nullptr;
+  int lwork = 0;
+  int* d_info = nullptr;
+  // multi-GPU
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  long long launches = 0;  // kernels launched by this handle (bench gpu_launches)
+};
+
+namespace mcba {
+
+void set_error(const std::string& msg);
+#define MCBA_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      mcba::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+      return MCBA_ERR_CUDA;                                                               \
+    }                                                                                     \
+  } while (0)
+
+// kernel launchers (defined in the .cu files)
+int launch_prep_cameras(mcba_handle* h, const double* x);
+int launch_tile_observations(mcba_handle* h);
+int ensure_row_offsets(mcba_handle* h);
+int launch_residuals(mcba_handle* h, const double* x, double* r_out);
+int launch_predict(mcba_handle* h, const double* x, double* uv_out);
+int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, double* out_scal);
+int launch_k2_frames(mcba_handle* h, const double* x, double lambda, int loss, double f_scale);
+int launch_k2_syrk(mcba_handle* h);
+int launch_finalize(mcba_handle* h);
+int launch_jacobian_blocks(mcba_handle* h, const double* x, double* Jc, double* Jp);
+int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda);
+int allreduce_packed(mcba_handle* h, double* buf, long long n);
+
+}  // namespace mcba

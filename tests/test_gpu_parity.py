@@ -1,0 +1,288 @@
+"""GPU parity tests: every call goes through the C ABI (libmcba.so) and is
+checked against the numpy oracle and the committed fixtures generated from the
+unmodified reference.  Tolerances are the ones BASELINE.json's north_star states:
+residuals 1e-10 relative, Jacobians 1e-5 relative to the reference's finite
+differences (norm-wise per column block), converged RMS within 1e-6 px and
+camera parameters within 1e-6 relative (gauge-normalised)."""
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+from conftest import load_golden, split_cams
+from oracle import np_oracle as orc
+import multicam_calibration_b200 as mcc
+from multicam_calibration_b200.synthetic import make_scene, make_keypoints
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+# ------------------------------------------------------------------ geometry / config 5
+def test_project_points_matches_reference():
+    g = load_golden("geometry")
+    uv = mcc.project_points(g["pts"], g["ext"], g["K"], g["dist"])
+    assert uv.shape == g["uv_dist"].shape
+    np.testing.assert_allclose(uv, g["uv_dist"], rtol=1e-12)
+    np.testing.assert_allclose(mcc.project_points(g["pts"], g["ext"], g["K"], None), g["uv_nodist"], rtol=1e-12)
+
+
+def test_undistort_points_matches_reference_cv2():
+    g = load_golden("geometry")
+    out = mcc.undistort_points(g["uv_in"], g["K"], g["dist"])
+    assert np.array_equal(np.isnan(out), np.isnan(g["uv_undist"]))
+    np.testing.assert_allclose(out, g["uv_undist"], rtol=0, atol=1e-9)
+
+
+def test_triangulate_matches_reference():
+    g = load_golden("triangulate")
+    intr = list(zip(g["Ks"], g["dists"]))
+    out = mcc.triangulate(list(g["all_uvs"]), list(g["extrinsics"]), intr)
+    assert np.array_equal(np.isnan(out), np.isnan(g["points"]))
+    np.testing.assert_allclose(out, g["points"], rtol=1e-8, atol=1e-8)
+
+
+def test_triangulate_large_against_oracle_and_truth():
+    all_uvs, ext, intr, pts = make_keypoints(20000, 6, sigma=0.0, p_missing=0.2, seed=2)
+    out = mcc.triangulate(all_uvs, list(ext), intr)
+    ref = orc.triangulate(all_uvs, list(ext), intr)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    ok = ~np.isnan(ref).any(1)
+    np.testing.assert_allclose(out[ok], ref[ok], rtol=1e-8, atol=1e-8)
+    # noise-free projections of (k1,k2)-distorted cameras: the 5-step undistortion is accurate to ~1e-6 px
+    assert np.abs(out[ok] - pts[ok]).max() < 1e-2
+    # round trip: project the triangulated points back
+    uv = mcc.project_points(out[ok], ext[0], *intr[0])
+    seen = ~np.isnan(all_uvs[0][ok]).any(1)
+    assert np.abs(uv[seen] - all_uvs[0][ok][seen]).max() < 1e-2
+
+
+# ------------------------------------------------------------------ per-call operators
+def test_residuals_match_reference_fixture():
+    g = load_golden("ba_small")
+    r = mcc.residuals(g["x0"], g["uvs"], g["objpoints"])
+    assert r.shape == g["residuals"].shape
+    assert rel(r, g["residuals"]) < 1e-10
+    assert np.abs(r - g["residuals"]).max() < 1e-10 * np.abs(g["residuals"]).max()
+
+
+def test_predict_and_embed_match_reference_fixture():
+    g = load_golden("ba_small")
+    ext, intr, poses = mcc.deserialize_params(g["x0"], g["uvs"].shape[0])
+    np.testing.assert_allclose(mcc.embed_calib_objpoints(g["objpoints"], poses), g["world"], rtol=1e-12, atol=1e-11)
+    np.testing.assert_allclose(mcc.predict_calib_uvs(ext, intr, g["objpoints"], poses), g["predicted"], rtol=1e-11)
+    prob = mcc.BAProblem(g["uvs"], g["objpoints"])
+    np.testing.assert_allclose(prob.predict(g["x0"]), g["predicted"], rtol=1e-11)
+    assert prob.n_residuals == g["residuals"].size
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 33, 4), (3, 64, 35), (9, 70, 6), (16, 40, 35)])
+def test_residuals_ragged_shapes_against_oracle(shape):
+    C, F, N = shape
+    sc = make_scene(C, F, board=(1, N) if N != 35 else (5, 7), sigma=0.5, p_missing_view=0.3,
+                    p_missing_corner=0.15, seed=C * 100 + F)
+    uvs = sc.uvs.copy()
+    if uvs.size > 8:
+        uvs[0, 0, 0, 1] = np.nan
+    x = sc.x0()
+    ref = orc.residuals(x, uvs, sc.objpoints)
+    out = mcc.residuals(x, uvs, sc.objpoints)
+    assert out.shape == ref.shape
+    if ref.size:
+        assert np.abs(out - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1.0)
+
+
+def test_residuals_all_missing_is_empty():
+    sc = make_scene(2, 5, sigma=0.1, seed=1)
+    uvs = np.full_like(sc.uvs, np.nan)
+    assert mcc.residuals(sc.x0(), uvs, sc.objpoints).shape == (0,)
+
+
+def test_jacobian_blocks_match_oracle_and_reference_fd():
+    g = load_golden("ba_small")
+    uvs, obj, x0 = g["uvs"], g["objpoints"], g["x0"]
+    C, F, N, _ = uvs.shape
+    prob = mcc.BAProblem(uvs, obj)
+    Jc, Jp = prob.jacobian_blocks(x0)
+    Jc_o, Jp_o, _ = orc.jacobian_blocks(x0, C, obj)
+    assert rel(Jc, -Jc_o) < 1e-11 and rel(Jp, -Jp_o) < 1e-11
+    # assemble in the reference row order and compare with ITS finite differences
+    ci, fi, ni, ui = np.nonzero(~np.isnan(uvs))
+    J = np.zeros((ci.size, 12 * C + 6 * F))
+    rows = np.arange(ci.size)
+    for s in range(12):
+        J[rows, ci * 12 + s] = Jc[ci, fi, ni, ui, s]
+    for s in range(6):
+        J[rows, 12 * C + fi * 6 + s] = Jp[ci, fi, ni, ui, s]
+    J2 = csr_matrix((g["J2_data"], g["J2_indices"], g["J2_indptr"]), shape=J.shape).toarray()
+    J3 = csr_matrix((g["J3_data"], g["J3_indices"], g["J3_indptr"]), shape=J.shape).toarray()
+    assert rel(J, J3) < 1e-8
+    for s in range(12):
+        cols = np.arange(C) * 12 + s
+        assert rel(J[:, cols], J2[:, cols]) < 1e-5
+    for s in range(6):
+        cols = 12 * C + np.arange(F) * 6 + s
+        assert rel(J[:, cols], J2[:, cols]) < 1e-5
+
+
+@pytest.mark.parametrize("loss", ["soft_l1", "linear"])
+@pytest.mark.parametrize("lam", [0.0, 1e-2])
+def test_reduced_camera_system_matches_oracle(loss, lam):
+    g = load_golden("ba_small")
+    uvs, obj, x0 = g["uvs"], g["objpoints"], g["x0"]
+    C = uvs.shape[0]
+    prob = mcc.BAProblem(uvs, obj)
+    S, b, gcam, cost = prob.build_reduced(x0, lam=lam, loss=loss)
+    H, grad, cost_o = orc.normal_equations(x0, uvs, obj, loss=loss)
+    D2 = np.diag(H).copy()
+    D2[:12 * C] = 0.0                    # camera damping is added by the solve, not by K2
+    S_o, b_o = orc.reduced_camera_system(H, grad, C, lam, D2)
+    assert cost == pytest.approx(cost_o, rel=1e-12)
+    assert rel(gcam, grad[:12 * C]) < 1e-10
+    assert np.abs(S - S_o).max() < 1e-9 * np.abs(S_o).max()
+    assert np.abs(b - b_o).max() < 1e-9 * np.abs(b_o).max()
+    assert np.abs(S - S.T).max() == 0.0
+    assert rel(prob.gradient(), grad) < 1e-10
+    c2, sumsq, cnt = prob.cost(x0, loss=loss)
+    assert c2 == pytest.approx(cost_o, rel=1e-12) and cnt == g["residuals"].size
+    assert sumsq == pytest.approx(float((g["residuals"] ** 2).sum()), rel=1e-11)
+
+
+def test_damped_step_matches_oracle():
+    g = load_golden("ba_small")
+    uvs, obj, x0 = g["uvs"], g["objpoints"], g["x0"]
+    C = uvs.shape[0]
+    lam = 1e-3
+    prob = mcc.BAProblem(uvs, obj)
+    prob.build_reduced(x0, lam=lam)
+    x1 = prob.solve_step(lam)
+    H, grad, _ = orc.normal_equations(x0, uvs, obj)
+    step = orc.lm_step(H, grad, C, lam, np.diag(H).copy())
+    assert np.abs((x1 - x0) - step).max() < 1e-7 * np.abs(step).max()
+
+
+def test_many_cameras_reduced_system_matches_oracle():
+    # 9 and 16 cameras exercise the camera-group path (more cameras than warps per CTA)
+    for C, F in ((9, 37), (16, 33)):
+        sc = make_scene(C, F, sigma=0.4, p_missing_view=0.3, seed=C)
+        x0 = sc.x0()
+        prob = mcc.BAProblem(sc.uvs, sc.objpoints)
+        lam = 1e-3
+        S, b, gcam, cost = prob.build_reduced(x0, lam=lam)
+        H, grad, cost_o = orc.normal_equations(x0, sc.uvs, sc.objpoints)
+        D2 = np.diag(H).copy()
+        D2[:12 * C] = 0.0
+        S_o, b_o = orc.reduced_camera_system(H, grad, C, lam, D2)
+        assert cost == pytest.approx(cost_o, rel=1e-12)
+        assert np.abs(S - S_o).max() < 1e-9 * np.abs(S_o).max()
+        assert np.abs(b - b_o).max() < 1e-9 * np.abs(b_o).max()
+        x1 = prob.solve_step(lam)
+        step = orc.lm_step(H, grad, C, lam, np.diag(H).copy())
+        assert np.abs((x1 - x0) - step).max() < 1e-6 * np.abs(step).max()
+
+
+# ------------------------------------------------------------------ convergence
+def gauge_free(x, C):
+    cams = x[:12 * C].reshape(C, 12)
+    return cams[:, :6].copy(), orc.relative_camera_transforms(cams[:, 6:])
+
+
+def test_converges_to_the_reference_minimum():
+    g = load_golden("convergence")
+    use = g["use_frames"]
+    uv, obj = g["uvs"][:, use], g["objpoints"]
+    C = uv.shape[0]
+    x0 = np.concatenate([g["init_cams"].ravel(), g["init_poses"][use].ravel()])
+    prob = mcc.BAProblem(uv, obj)
+    x, res = prob.solve(x0, ftol=1e-15, xtol=1e-15, gtol=1e-9, max_nfev=300, verbose=0)
+    rms = orc.reprojection_rms(x, uv, obj)
+    assert res.cost <= float(g["cost_tight"]) * (1 + 1e-10)
+    assert abs(rms - float(g["rms_tight"])) < 1e-6
+    assert abs(res.rms - rms) < 1e-9
+    assert res.optimality < 1e-6
+    # the engine's own minimum against scipy polished from it: parameters agree (gauge-normalised)
+    from scipy.optimize import least_squares
+    pol = least_squares(orc.residuals, x, jac=lambda p, u, o: orc.analytic_jac_for_scipy(p, u, o).toarray(),
+                        args=(uv, obj), method="trf", loss="soft_l1", x_scale="jac", tr_solver="exact",
+                        ftol=1e-15, xtol=1e-15, gtol=1e-15, max_nfev=30, verbose=0)
+    assert abs(orc.reprojection_rms(pol.x, uv, obj) - rms) < 1e-6
+    intr_a, T_a = gauge_free(x, C)
+    intr_b, T_b = gauge_free(pol.x, C)
+    np.testing.assert_allclose(intr_a, intr_b, rtol=1e-6)
+    assert np.abs(T_a - T_b).max() < 1e-6 * np.abs(T_b).max()
+    # and against the fixture produced with the unmodified reference residual function
+    intr_t, T_t = gauge_free(g["x_tight"], C)
+    np.testing.assert_allclose(intr_a[:, :4], intr_t[:, :4], rtol=1e-5)
+    assert np.abs(T_a - T_t).max() < 1e-4 * np.abs(T_t).max()
+
+
+def test_default_tolerances_reach_at_least_the_reference_cost():
+    g = load_golden("convergence")
+    use = g["use_frames"]
+    uv, obj = g["uvs"][:, use], g["objpoints"]
+    x0 = np.concatenate([g["init_cams"].ravel(), g["init_poses"][use].ravel()])
+    x, res = mcc.BAProblem(uv, obj).solve(x0, verbose=0)
+    assert res.status in (1, 2, 3, 4) and res.success
+    assert res.cost <= float(g["cost_default"]) * (1 + 1e-6)
+    assert res.fun.shape == ((~np.isnan(uv)).sum(),)
+    assert res.cost == pytest.approx(orc.robust_cost(x, uv, obj), rel=1e-10)
+    np.testing.assert_allclose(res.grad, orc.normal_equations(x, uv, obj)[1], atol=1e-7 * np.abs(res.grad).max() + 1e-9)
+
+
+def test_bundle_adjust_api_matches_reference_front_end(capsys):
+    g = load_golden("frontend")
+    ext, intr = split_cams(g["init_cams"])
+    for tag, nf in (("all", None), ("sub", 20)):
+        np.random.seed(0)
+        e, i, p, use, result = mcc.bundle_adjust(g["uvs"], ext, intr, g["objpoints"], g["init_poses"],
+                                                 n_frames=nf, verbose=0)
+        out = capsys.readouterr().out
+        assert np.array_equal(use, g[f"use_{tag}"])
+        assert out.strip().splitlines()[0] == str(g[f"msg_{tag}"]).strip()
+        assert e.shape == (5, 6) and p.shape == (len(use), 6) and len(i) == 5
+        assert i[0][0].shape == (3, 3) and i[0][1].shape == (5,)
+        assert result.x.shape == (60 + 6 * len(use),) and result.success
+
+
+def test_bundle_adjust_verbose_table_and_nonfinite_x0(capsys):
+    sc = make_scene(3, 12, sigma=0.2, seed=4)
+    args = sc.init_args()
+    mcc.bundle_adjust(*args, n_frames=None, max_nfev=5)
+    out = capsys.readouterr().out
+    assert "Iteration" in out and "Total nfev" in out and "Optimality" in out
+    bad = args[4].copy()
+    bad[3, 0] = np.nan
+    with pytest.raises(ValueError, match="not finite"):
+        mcc.BAProblem(sc.uvs, sc.objpoints).solve(np.concatenate([sc.init_cams.ravel(), bad.ravel()]), verbose=0)
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_cfg2():
+    """6 cams x 5000 frames: size-independent checks (no oracle at this size)."""
+    sc = make_scene(6, 5000, sigma=0.3, p_missing_view=0.2, seed=0)
+    prob = mcc.BAProblem(sc.uvs, sc.objpoints)
+    x0 = sc.x0()
+    # (1) cost from K2, from the cost kernel and from the materialised residual vector agree
+    r = prob.residuals(x0)
+    cost_r = float((2 * (np.sqrt(1 + r * r) - 1)).sum() * 0.5)
+    S, b, gcam, cost = prob.build_reduced(x0, lam=1e-3)
+    assert cost == pytest.approx(cost_r, rel=1e-11)
+    assert prob.cost(x0)[0] == pytest.approx(cost_r, rel=1e-11)
+    assert r.size == (~np.isnan(sc.uvs)).sum()
+    # (2) sharding additivity: S, b of two halves (same camera block) sum to the whole
+    halves = []
+    for a, bnd in ((0, 2500), (2500, 5000)):
+        p2 = mcc.BAProblem(sc.uvs[:, a:bnd], sc.objpoints)
+        xl = np.concatenate([x0[:72], x0[72 + 6 * a:72 + 6 * bnd]])
+        halves.append(p2.build_reduced(xl, lam=1e-3))
+    S2 = halves[0][0] + halves[1][0]
+    b2 = halves[0][1] + halves[1][1]
+    assert np.abs(S2 - S).max() < 1e-11 * np.abs(S).max()
+    assert np.abs(b2 - b).max() < 1e-10 * np.abs(b).max()
+    # (3) the solve reduces the cost monotonically to the noise floor and is a stationary point
+    x, res = prob.solve(x0, ftol=1e-10, verbose=0)
+    assert res.cost < cost and res.success
+    assert 0.28 < res.rms < 0.32          # sigma = 0.3 px
+    assert res.optimality < 1e-2 * np.abs(gcam).max()

@@ -1,0 +1,145 @@
+"""CPU: host-side logic, the C-ABI surface and the multi-rank plumbing (gloo)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, split_cams
+from oracle import np_oracle as orc
+import multicam_calibration_b200 as mcc
+from multicam_calibration_b200 import _native, distributed, engine
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mcba.h")).read()
+    declared = set(re.findall(r"\b(mcba_[a-z_0-9]+)\s*\(", header))
+    declared -= {"mcba_handle", "mcba_options", "mcba_result"}
+    assert declared, "no prototypes found"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/mcba.h but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    assert _native.load().mcba_version() >= 100
+
+
+def test_default_options_follow_the_reference_defaults():
+    o = _native.Options()
+    _native.load().mcba_default_options(ctypes.byref(o))
+    assert (o.ftol, o.xtol, o.gtol, o.loss, o.verbose) == (1e-4, 1e-8, 1e-8, 1, 2)   # bundle_adjustment.py:301-303
+    o2 = engine.parse_options(dict(ftol=1e-9, loss="linear", max_nfev=7, verbose=0), 100)
+    assert (o2.ftol, o2.loss, o2.max_nfev, o2.verbose) == (1e-9, 0, 7, 0)
+    for bad in (dict(jac="3-point"), dict(tr_solver="exact"), dict(bounds=(0, 1))):
+        with pytest.raises(TypeError):
+            engine.parse_options(bad, 10)
+    with pytest.raises(ValueError):
+        engine.parse_options(dict(loss="huber"), 10)
+    with pytest.raises(ValueError):
+        engine.parse_options(dict(x_scale=1.0), 10)
+
+
+def test_no_cuda_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    g = load_golden("ba_small")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mcc.residuals(g["x0"], g["uvs"], g["objpoints"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mcc.project_points(np.zeros((3, 3)), np.zeros(6), np.eye(3))
+
+
+def test_serialize_roundtrip_and_layout():
+    g = load_golden("ba_small")
+    x0 = g["x0"]
+    C = g["uvs"].shape[0]
+    ext, intr, poses = mcc.deserialize_params(x0, C)
+    ext_o, intr_o, poses_o = orc.deserialize_params(x0, C)
+    assert np.array_equal(ext, ext_o) and np.array_equal(poses, poses_o)
+    for (K, d), (Ko, do) in zip(intr, intr_o):
+        assert np.array_equal(K, Ko) and np.array_equal(d, do) and d.shape == (5,)
+    assert np.array_equal(mcc.serialize_params(ext, intr, poses), x0)
+
+
+def test_sparsity_pattern_matches_reference():
+    g = load_golden("ba_small")
+    A = mcc.bundle_adjustment_sparsity(g["uvs"]).tocsr()
+    A.sort_indices()
+    assert np.array_equal(A.indices, g["A_indices"]) and np.array_equal(A.indptr, g["A_indptr"])
+    assert (A.sum(1) == 18).all()
+
+
+def test_host_geometry_helpers_match_reference():
+    g = load_golden("geometry")
+    np.testing.assert_allclose(mcc.rodrigues(g["r"]), g["R"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(mcc.rodrigues_inv(g["R"]), g["r_back"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(mcc.get_transformation_matrix(g["t6"]), g["T"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(mcc.get_transformation_vector(g["T"]), g["t6_back"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(mcc.apply_rigid_transform(g["ext"], g["pts"]), g["pts_rigid_vec"], rtol=1e-14)
+    np.testing.assert_allclose(mcc.apply_rigid_transform(g["T"][3], g["pts"][3]),
+                               orc.apply_rigid_transform(g["T"][3], g["pts"][3]), rtol=1e-14)
+    np.testing.assert_allclose(mcc.get_projection_matrix(g["ext"], (g["K"], g["dist"])), g["P"], rtol=1e-14)
+    h = mcc.euclidean_to_homogenous(g["pts"])
+    assert h.shape[-1] == 4 and (h[..., 3] == 1).all()
+    np.testing.assert_allclose(mcc.homogeneous_to_euclidean(h * 3.0), g["pts"], rtol=1e-15)
+    t, rmsd = mcc.rigid_transform_from_correspondences(g["pts"][0], g["pts_rigid_vec"][0])
+    np.testing.assert_allclose(t, g["ext"], atol=1e-9)
+    assert rmsd < 1e-9
+
+
+def test_shard_bounds_partition_frames():
+    for F, W in ((10, 3), (50000, 8), (8, 8), (33, 2)):
+        spans = [distributed.shard_bounds(F, W, r) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == F
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    x = np.arange(12 * 2 + 6 * 7, dtype=float)
+    parts = [distributed.split_params(x, 2, *distributed.shard_bounds(7, 3, r)) for r in range(3)]
+    assert np.array_equal(distributed.merge_params(parts[0][:24], [p[24:] for p in parts]), x)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch
+        g = load_golden("ba_small")
+        uvs, obj, x0 = g["uvs"], g["objpoints"], g["x0"]
+        C, F = uvs.shape[:2]
+        a, b = distributed.shard_bounds(F, world, rank)
+        assert distributed.world_size() == world and distributed.rank() == rank
+        # each rank's reduced camera system (oracle arithmetic) summed over ranks == the full one:
+        # the camera block U is additive over frames, and so are the Schur corrections
+        xl = distributed.split_params(x0, C, a, b)
+        H, grad, cost = orc.normal_equations(xl, uvs[:, a:b], obj)
+        S, bb = orc.reduced_camera_system(H, grad, C)
+        packed = torch.from_numpy(np.concatenate([S.ravel(), bb, [cost]]))
+        dist.all_reduce(packed)
+        poses = distributed.gather_arrays(xl[12 * C:])
+        x_back = distributed.merge_params(xl[:12 * C], poses)
+        if rank == 0:
+            Hf, gf, cf = orc.normal_equations(x0, uvs, obj)
+            Sf, bf = orc.reduced_camera_system(Hf, gf, C)
+            full = np.concatenate([Sf.ravel(), bf, [cf]])
+            err = np.abs(packed.numpy() - full).max() / np.abs(full).max()
+            q.put((err, bool(np.array_equal(x_back, x0))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_sharding_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, same = q.get(timeout=180)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert err < 1e-12 and same

@@ -1,0 +1,103 @@
+"""CPU: the numpy oracle reproduces the outputs of the unmodified reference
+(fixtures written by tests/golden/make_golden.py in the build container)."""
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+from conftest import load_golden, split_cams
+from oracle import np_oracle as orc
+
+
+def test_geometry_matches_reference():
+    g = load_golden("geometry")
+    assert np.array_equal(orc.rodrigues(g["r"]), g["R"])
+    np.testing.assert_allclose(orc.rodrigues_inv(g["R"]), g["r_back"], rtol=0, atol=1e-14)
+    assert np.array_equal(orc.transformation_matrix(g["t6"]), g["T"])
+    np.testing.assert_allclose(orc.transformation_vector(g["T"]), g["t6_back"], rtol=0, atol=1e-12)
+    ext, K, dist, pts = g["ext"], g["K"], g["dist"], g["pts"]
+    assert np.array_equal(orc.apply_rigid_transform(ext, pts), g["pts_rigid_vec"])
+    assert np.array_equal(orc.apply_rigid_transform(orc.transformation_matrix(ext), pts), g["pts_rigid_mat"])
+    np.testing.assert_allclose(orc.project_points(pts, ext, K, dist), g["uv_dist"], rtol=1e-14)
+    np.testing.assert_allclose(orc.project_points(pts, ext, K, None), g["uv_nodist"], rtol=1e-14)
+    np.testing.assert_allclose(orc.projection_matrix(ext, (K, dist)), g["P"], rtol=1e-15)
+    und = orc.undistort_points(g["uv_in"], K, dist)
+    assert np.array_equal(np.isnan(und), np.isnan(g["uv_undist"]))
+    np.testing.assert_allclose(und, g["uv_undist"], rtol=0, atol=1e-9)
+
+
+def test_rodrigues_theta_zero_is_identity():
+    assert np.array_equal(orc.rodrigues(np.zeros(3)), np.eye(3))
+
+
+def test_triangulate_matches_reference():
+    g = load_golden("triangulate")
+    intr = list(zip(g["Ks"], g["dists"]))
+    out = orc.triangulate(list(g["all_uvs"]), list(g["extrinsics"]), intr)
+    assert np.array_equal(np.isnan(out), np.isnan(g["points"]))
+    assert np.isnan(g["points"][:4]).all()          # < 2 views
+    np.testing.assert_allclose(out, g["points"], rtol=1e-9, atol=1e-9)
+
+
+def test_residuals_and_layout_match_reference():
+    g = load_golden("ba_small")
+    uvs, obj, x0 = g["uvs"], g["objpoints"], g["x0"]
+    r = orc.residuals(x0, uvs, obj)
+    assert r.shape == g["residuals"].shape == ((~np.isnan(uvs)).sum(),)
+    np.testing.assert_allclose(r, g["residuals"], rtol=0, atol=1e-12)
+    ext, intr, poses = orc.deserialize_params(x0, uvs.shape[0])
+    np.testing.assert_allclose(orc.predict_calib_uvs(ext, intr, obj, poses), g["predicted"], rtol=1e-14)
+    np.testing.assert_allclose(orc.embed_calib_objpoints(obj, poses), g["world"], rtol=1e-14, atol=1e-13)
+    assert np.array_equal(orc.serialize_params(ext, intr, poses), x0)
+    A = orc.sparsity_pattern(uvs)
+    assert np.array_equal(A.indices, g["A_indices"]) and np.array_equal(A.indptr, g["A_indptr"])
+
+
+def test_analytic_jacobian_matches_reference_finite_differences():
+    g = load_golden("ba_small")
+    uvs, obj, x0 = g["uvs"], g["objpoints"], g["x0"]
+    J = orc.dense_residual_jacobian(x0, uvs, obj)
+    shape = J.shape
+    J3 = csr_matrix((g["J3_data"], g["J3_indices"], g["J3_indptr"]), shape=shape).toarray()
+    J2 = csr_matrix((g["J2_data"], g["J2_indices"], g["J2_indptr"]), shape=shape).toarray()
+    assert np.linalg.norm(J - J3) / np.linalg.norm(J3) < 1e-8
+    C = uvs.shape[0]
+    # 1e-5 relative, norm-wise per parameter column block
+    for s in range(12):
+        cols = np.arange(C) * 12 + s
+        assert np.linalg.norm(J[:, cols] - J2[:, cols]) <= 1e-5 * np.linalg.norm(J2[:, cols])
+    for s in range(6):
+        cols = 12 * C + np.arange((shape[1] - 12 * C) // 6) * 6 + s
+        assert np.linalg.norm(J[:, cols] - J2[:, cols]) <= 1e-5 * np.linalg.norm(J2[:, cols])
+
+
+def test_frame_selection_matches_reference(capsys):
+    g = load_golden("frontend")
+    ext, intr = split_cams(g["init_cams"])
+    for tag, nf in (("all", None), ("sub", 20)):
+        np.random.seed(0)
+        use, _ = orc.select_frames(g["uvs"], ext, intr, g["objpoints"], g["init_poses"], n_frames=nf)
+        assert np.array_equal(use, g[f"use_{tag}"])
+        assert capsys.readouterr().out.strip() == str(g[f"msg_{tag}"]).strip()
+    assert 17 not in g["use_all"]
+
+
+def test_schur_step_equals_dense_step():
+    g = load_golden("ba_small")
+    uvs, obj, x0 = g["uvs"], g["objpoints"], g["x0"]
+    C = uvs.shape[0]
+    H, grad, cost = orc.normal_equations(x0, uvs, obj)
+    D2 = np.diag(H).copy()
+    lam = 1e-3
+    step = orc.lm_step(H, grad, C, lam, D2)
+    dense = -np.linalg.solve(H + lam * np.diag(D2), grad)
+    np.testing.assert_allclose(step, dense, rtol=1e-7, atol=1e-9 * np.abs(dense).max())
+    assert cost == pytest.approx(orc.robust_cost(x0, uvs, obj))
+
+
+def test_convergence_fixture_is_a_stationary_point():
+    g = load_golden("convergence")
+    uv = g["uvs"][:, g["use_frames"]]
+    H, grad, cost = orc.normal_equations(g["x_tight"], uv, g["objpoints"])
+    assert cost == pytest.approx(float(g["cost_tight"]), rel=1e-12)
+    assert float(g["cost_tight"]) <= float(g["cost_default"])
+    assert orc.reprojection_rms(g["x_tight"], uv, g["objpoints"]) == pytest.approx(float(g["rms_tight"]), rel=1e-12)
