@@ -157,6 +157,12 @@ int mcba_triangulate(int device, void* cuda_stream, const double* d_uvs, int n_c
                      int64_t n_points, const double* h_ext, const double* h_K,
                      const double* h_dist, double* d_points);
 
+/* Per-kernel device timing of the evaluation pass (CUDA events on the handle's stream).
+ * Synchronises, returns in ms_out[3] the summed durations of {K2a frames, K2b SYRK,
+ * finalize + all-reduce} over the n evaluations since the last call, resets the
+ * counters and switches recording on/off. */
+int mcba_profile(mcba_handle* h, int enable, double* ms_out, int* n_out);
+
 /* Number of kernels this handle has launched (bench.py gpu_launches). */
 int64_t mcba_kernel_launches(mcba_handle* h);
 

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "mcba_undistort_points": (_I, [_I, _P, _P, _L, _P, _P, _P]),
     "mcba_triangulate": (_I, [_I, _P, _P, _I, _L, _P, _P, _P, _P]),
     "mcba_kernel_launches": (_L, [_P]),
+    "mcba_profile": (_I, [_P, _I, ctypes.POINTER(_D), ctypes.POINTER(_I)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

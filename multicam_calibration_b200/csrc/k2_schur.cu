@@ -209,8 +209,10 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
 #pragma unroll
     for (int k = 0; k < 12; ++k) s += Tc[k * 12 + i] * X[k * 12 + j];
     const int r = 12 * c + i, q = 12 * cp + j;
-    p.red[p.offS + (size_t)r * p.nc + q] = s;
-    p.red[p.offS + (size_t)q * p.nc + r] = s;
+    if (c != cp || i <= j) {   // diagonal blocks: one thread writes both mirror entries (exact symmetry)
+      p.red[p.offS + (size_t)r * p.nc + q] = s;
+      p.red[p.offS + (size_t)q * p.nc + r] = s;
+    }
   }
   if (c != cp) return;
   // diagonal block extras: diag(T^T U_raw T), b, g_cam

@@ -68,11 +68,17 @@ struct EvalOut {
 // residual + Jacobian + Schur at x; the packed system is left (all-reduced) in d_red
 static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, double f_scale) {
   int rc;
+  const bool prof = h->profile && h->prof_n < kProfRing;
+  cudaEvent_t* ev = prof ? h->prof_ev + 4 * h->prof_n : nullptr;
   if ((rc = launch_prep_cameras(h, x))) return rc;
+  if (prof) cudaEventRecord(ev[0], h->stream);
   if ((rc = launch_k2_frames(h, x, lambda, loss, f_scale))) return rc;
+  if (prof) cudaEventRecord(ev[1], h->stream);
   if ((rc = launch_k2_syrk(h))) return rc;
+  if (prof) cudaEventRecord(ev[2], h->stream);
   if ((rc = launch_finalize(h))) return rc;
   if ((rc = allreduce_packed(h, h->d_red, h->L.redLen))) return rc;
+  if (prof) { cudaEventRecord(ev[3], h->stream); h->prof_n++; }
   return MCBA_OK;
 }
 
@@ -207,6 +213,10 @@ int mcba_destroy(mcba_handle* h) {
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
                   h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->prof_ev) {
+    for (int i = 0; i < 4 * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);
+    delete[] h->prof_ev;
+  }
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -309,7 +319,7 @@ int mcba_build_reduced(mcba_handle* h, const double* d_x, double lambda, int los
   if (h_b) MCBA_CUDA(cudaMemcpyAsync(h_b, h->d_red + L.offB, sizeof(double) * L.nc, cudaMemcpyDeviceToHost, h->stream));
   if (h_gcam) MCBA_CUDA(cudaMemcpyAsync(h_gcam, h->d_red + L.offG, sizeof(double) * L.nc, cudaMemcpyDeviceToHost, h->stream));
   if (h_cost) MCBA_CUDA(cudaMemcpyAsync(h_cost, h->d_red + L.offScal + kRsCost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (h_S || h_b || h_gcam || h_cost) MCBA_CUDA(cudaStreamSynchronize(h->stream));   // no outputs: stay asynchronous
   return MCBA_OK;
 }
 
@@ -492,5 +502,30 @@ int mcba_comm_init(mcba_handle* h, const void* id128, int rank, int nranks) {
 }
 
 int64_t mcba_kernel_launches(mcba_handle* h) { return h ? h->launches : 0; }
+
+int mcba_profile(mcba_handle* h, int enable, double* ms_out, int* n_out) {
+  if (!h) return MCBA_ERR_ARG;
+  MCBA_CUDA(cudaSetDevice(h->device));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (ms_out) {
+    double acc[3] = {0, 0, 0};
+    for (int i = 0; i < h->prof_n; ++i) {
+      for (int k = 0; k < 3; ++k) {
+        float ms = 0;
+        MCBA_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[4 * i + k], h->prof_ev[4 * i + k + 1]));
+        acc[k] += ms;
+      }
+    }
+    for (int k = 0; k < 3; ++k) ms_out[k] = acc[k];
+  }
+  if (n_out) *n_out = h->prof_n;
+  h->prof_n = 0;
+  if (enable && !h->prof_ev) {
+    h->prof_ev = new cudaEvent_t[4 * kProfRing];
+    for (int i = 0; i < 4 * kProfRing; ++i) MCBA_CUDA(cudaEventCreate(&h->prof_ev[i]));
+  }
+  h->profile = enable != 0;
+  return MCBA_OK;
+}
 
 }  // extern "C"

@@ -22,6 +22,7 @@ enum RedScalar : int {
 };
 
 constexpr int kMaxRanks = 64;
+constexpr int kProfRing = 2048;
 constexpr int kUPad = 96;  // 78 (A upper triangle) + 12 (q) padded to 3 x 32
 
 struct Layout {
@@ -97,6 +98,10 @@ struct mcba_handle {
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
   long long launches = 0;  // kernels launched by this handle (bench gpu_launches)
+  // optional per-kernel timing (CUDA events on the launching stream; bench.py roofline)
+  bool profile = false;
+  cudaEvent_t* prof_ev = nullptr;   // ring of 4 events per evaluation
+  int prof_n = 0;
 };
 
 namespace mcba {

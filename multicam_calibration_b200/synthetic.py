@@ -93,7 +93,9 @@ class Scene:
 
 
 def make_scene(n_cameras=6, n_frames=500, board=(5, 7), square=12.5, sigma=0.3,
-               p_missing_view=0.0, p_missing_corner=0.0, seed=0, perturb=1.0):
+               p_missing_view=0.0, p_missing_corner=0.0, seed=0, perturb=1.0, shard=0):
+    """``seed`` fixes the cameras; ``(seed, shard)`` fixes the frames, so ranks that
+    generate different shards of one scene share the cameras."""
     rng = np.random.default_rng(seed)
     obj = chessboard_objpoints(board, square)
     C = n_cameras
@@ -114,6 +116,12 @@ def make_scene(n_cameras=6, n_frames=500, board=(5, 7), square=12.5, sigma=0.3,
     cams[:, 3] = rng.normal(512, 5, C)
     cams[:, 4] = rng.normal(-0.1, 0.02, C)
     cams[:, 5] = rng.normal(0.05, 0.01, C)
+    init_cams = cams.copy()
+    init_cams[:, 6:9] += perturb * rng.normal(0, 0.01, (C, 3))
+    init_cams[:, 9:12] += perturb * rng.normal(0, 3, (C, 3))
+    init_cams[:, 0:2] += perturb * rng.uniform(-10, 10, (C, 2))
+    init_cams[:, 4:6] *= 1 - 0.5 * min(perturb, 1.0)
+    rng = np.random.default_rng([seed, 1, shard])
     poses = np.concatenate([rng.normal(0, 0.6, (n_frames, 3)),
                             rng.normal(0, 60, (n_frames, 3))], axis=1)
     uvs = forward_model(cams, poses, obj)
@@ -123,11 +131,6 @@ def make_scene(n_cameras=6, n_frames=500, board=(5, 7), square=12.5, sigma=0.3,
         uvs[rng.random((C, n_frames)) < p_missing_view] = np.nan
     if p_missing_corner:
         uvs[rng.random(uvs.shape[:3]) < p_missing_corner] = np.nan
-    init_cams = cams.copy()
-    init_cams[:, 6:9] += perturb * rng.normal(0, 0.01, (C, 3))
-    init_cams[:, 9:12] += perturb * rng.normal(0, 3, (C, 3))
-    init_cams[:, 0:2] += perturb * rng.uniform(-10, 10, (C, 2))
-    init_cams[:, 4:6] *= 1 - 0.5 * min(perturb, 1.0)
     init_poses = poses.copy()
     init_poses[:, :3] += perturb * rng.normal(0, 0.02, (n_frames, 3))
     init_poses[:, 3:] += perturb * rng.normal(0, 2, (n_frames, 3))
