@@ -36,6 +36,13 @@ extern "C" {
 
 #define MCBA_LOSS_LINEAR 0
 #define MCBA_LOSS_SOFT_L1 1
+/* OR-ed into a loss code: Gauss-Newton weight rho' (IRLS majoriser) instead of scipy's
+ * rho' + 2 rho'' z (common.py:720-731).  Gradient, cost and fixed point are unchanged. */
+#define MCBA_LOSS_IRLS 0x100
+
+#define MCBA_HESSIAN_AUTO 0   /* IRLS while the cost still drops by > 1 % per step, then Triggs */
+#define MCBA_HESSIAN_TRIGGS 1 /* scipy's scaling throughout */
+#define MCBA_HESSIAN_IRLS 2
 
 typedef struct mcba_handle mcba_handle;
 
@@ -51,7 +58,7 @@ typedef struct mcba_options {
   int32_t loss;     /* MCBA_LOSS_* ; reference default soft_l1 */
   double f_scale;   /* scipy default 1.0 */
   int32_t verbose;  /* 0 silent, 1 summary, 2 per-iteration table (reference default 2) */
-  int32_t reserved;
+  int32_t hessian;  /* MCBA_HESSIAN_*: Gauss-Newton weights of the robust loss (default AUTO) */
   double lambda0;   /* initial damping, relative to the Jacobian scaling; <= 0: 1e-3 */
   double lambda_min;
   double lambda_max;

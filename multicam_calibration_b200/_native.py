@@ -13,7 +13,8 @@ CSRC = os.path.join(_HERE, "csrc")
 
 MCBA_OK = 0
 ERR_NONFINITE = -4
-LOSSES = {"linear": 0, "soft_l1": 1}
+LOSSES = {"linear": 0, "soft_l1": 1, "soft_l1_irls": 0x101}
+HESSIANS = {"auto": 0, "triggs": 1, "irls": 2}
 
 ITER_CALLBACK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                  ctypes.c_double, ctypes.c_double, ctypes.c_double)
@@ -22,7 +23,7 @@ ITER_CALLBACK = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_i
 class Options(ctypes.Structure):
     _fields_ = [("ftol", ctypes.c_double), ("xtol", ctypes.c_double), ("gtol", ctypes.c_double),
                 ("max_nfev", ctypes.c_int32), ("loss", ctypes.c_int32), ("f_scale", ctypes.c_double),
-                ("verbose", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("verbose", ctypes.c_int32), ("hessian", ctypes.c_int32),
                 ("lambda0", ctypes.c_double), ("lambda_min", ctypes.c_double),
                 ("lambda_max", ctypes.c_double), ("iter_callback", ITER_CALLBACK),
                 ("callback_user", ctypes.c_void_p)]

@@ -299,9 +299,11 @@ __global__ void __launch_bounds__(256, 1) k2_frames_kernel(const K2Params p) {
         double* lo = p.Linv + (size_t)tile * 21 * 32 + lane;
 #pragma unroll
         for (int i = 0; i < 21; ++i) lo[i * 32] = Linv[i];
-        double* yo = p.y + (size_t)tile * 6 * 32 + lane;
+        if (fvalid) {
+          double* yo = p.y + (size_t)f * 6;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) yo[i * 32] = yv[i];
+          for (int i = 0; i < 6; i += 2) *reinterpret_cast<double2*>(yo + i) = make_double2(yv[i], yv[i + 1]);
+        }
       }
     }
 

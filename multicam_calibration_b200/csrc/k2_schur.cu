@@ -12,48 +12,97 @@ __host__ __device__ constexpr int tri12s(int i, int j) {
 }
 
 // ------------------------------------------------------------------ SYRK
-// Thread-tile t < nT owns the 6x6 block (bi <= bj) of S_raw; thread-tiles
-// nT .. nT+nb-1 own 6 entries of Z y.  The K axis is (frame, pose column).
-__global__ void __launch_bounds__(288) k2_syrk_kernel(const double* __restrict__ Z, const double* __restrict__ y,
-                                                      int nc, int nb, int nT, long long F, int FB,
-                                                      long long frames_per_cta, double* __restrict__ part) {
-  extern __shared__ double smem[];
-  double* slab = smem;                              // [FB*6][nc]
-  double* ysm = slab + (size_t)FB * 6 * nc;         // [FB*6]
-  const int t = blockIdx.y * blockDim.x + threadIdx.x;
+// S_raw = sum_f Z_f Z_f^T (upper block triangle) and sum_f Z_f y_f.
+// Slot s < nT owns the 6x6 block (bi <= bj) of S_raw, slots nT .. nT+nb-1 own 6 entries
+// of Z y.  The K axis (frame, pose column) is split over KG thread groups; each
+// persistent CTA streams its contiguous range of Z through a 2-stage shared-memory
+// ring filled by TMA bulk copies (cp.async.bulk + mbarrier) so loads overlap the FMAs.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+constexpr int kSyrkStages = 2;
+
+__global__ void __launch_bounds__(384, 1) k2_syrk_kernel(const double* __restrict__ Z, const double* __restrict__ y,
+                                                         int nc, int nb, int nT, long long F, int FB, int slots_pad,
+                                                         int KG, long long frames_per_cta, double* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t slab_doubles = (size_t)FB * 6 * nc;
+  const size_t stage_doubles = slab_doubles + (size_t)FB * 6;     // Z slab + y slab
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  __shared__ unsigned long long full_bar[kSyrkStages];
+
+  const int slot_local = threadIdx.x % slots_pad, kg = threadIdx.x / slots_pad;
+  const int slot = blockIdx.y * slots_pad + slot_local;
   int kind = 2, bi = 0, bj = 0;
-  if (t < nT) {
+  if (slot_local < slots_pad && slot < nT) {
     kind = 0;
-    // decode the triangular index
-    int rem = t;
+    int rem = slot;
     while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
     bj = bi + rem;
-  } else if (t < nT + nb) {
+  } else if (slot < nT + nb) {
     kind = 1;
-    bi = t - nT;
+    bi = slot - nT;
   }
   double acc[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+
   const long long f_begin = blockIdx.x * frames_per_cta;
   long long f_end = f_begin + frames_per_cta;
   if (f_end > F) f_end = F;
-  for (long long f0 = f_begin; f0 < f_end; f0 += FB) {
+  const int n_chunks = f_end > f_begin ? (int)((f_end - f_begin + FB - 1) / FB) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSyrkStages; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int chunk) {
+    const int s = chunk % kSyrkStages;
+    const long long f0 = f_begin + (long long)chunk * FB;
     const int nfr = (int)((f_end - f0) < FB ? (f_end - f0) : FB);
-    const int nk = nfr * 6;
-    const double2* src = reinterpret_cast<const double2*>(Z + (size_t)f0 * 6 * nc);
-    double2* dst = reinterpret_cast<double2*>(slab);
-    for (int i = threadIdx.x; i < nk * nc / 2; i += blockDim.x) dst[i] = __ldcs(src + i);
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-      const long long f = f0 + i / 6;
-      ysm[i] = y[(f / kTile) * 6 * kTile + (i % 6) * kTile + (f % kTile)];
-    }
-    __syncthreads();
+    double* dst = stages + (size_t)s * stage_doubles;
+    const unsigned zb = (unsigned)(nfr * 6 * nc * sizeof(double)), yb = (unsigned)(nfr * 6 * sizeof(double));
+    mbar_expect_tx(&full_bar[s], zb + yb);
+    tma_load_1d(dst, Z + (size_t)f0 * 6 * nc, zb, &full_bar[s]);
+    tma_load_1d(dst + slab_doubles, y + (size_t)f0 * 6, yb, &full_bar[s]);
+  };
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < kSyrkStages && c < n_chunks; ++c) issue(c);
+  }
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int s = chunk % kSyrkStages;
+    mbar_wait(&full_bar[s], (unsigned)((chunk / kSyrkStages) & 1));
+    const long long f0 = f_begin + (long long)chunk * FB;
+    const int nk = (int)((f_end - f0) < FB ? (f_end - f0) : FB) * 6;
+    const double* slab = stages + (size_t)s * stage_doubles;
     if (kind == 0) {
       const double* ra = slab + 6 * bi;
       const double* rb = slab + 6 * bj;
 #pragma unroll 2
-      for (int kk = 0; kk < nk; ++kk) {
+      for (int kk = kg; kk < nk; kk += KG) {
         const double2 a0 = *reinterpret_cast<const double2*>(ra + (size_t)kk * nc);
         const double2 a1 = *reinterpret_cast<const double2*>(ra + (size_t)kk * nc + 2);
         const double2 a2 = *reinterpret_cast<const double2*>(ra + (size_t)kk * nc + 4);
@@ -69,43 +118,72 @@ __global__ void __launch_bounds__(288) k2_syrk_kernel(const double* __restrict__
       }
     } else if (kind == 1) {
       const double* ra = slab + 6 * bi;
-      for (int kk = 0; kk < nk; ++kk) {
+      const double* ysm = slab + slab_doubles;
+      for (int kk = kg; kk < nk; kk += KG) {
         const double yk = ysm[kk];
 #pragma unroll
         for (int i = 0; i < 6; ++i) acc[i] = fma(ra[(size_t)kk * nc + i], yk, acc[i]);
       }
     }
-    __syncthreads();
+    __syncthreads();   // everyone is done with stage s: refill it
+    if (threadIdx.x == 0 && chunk + kSyrkStages < n_chunks) issue(chunk + kSyrkStages);
   }
+
+  // reduce the KG partial accumulators through shared memory, then one partial per CTA
+  double* red = stages;   // [KG][slots_pad][36]
+  if (kind != 2) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) red[((size_t)kg * slots_pad + slot_local) * 36 + i] = acc[i];
+  }
+  __syncthreads();
   double* out = part + (size_t)blockIdx.x * ((size_t)nT * 36 + (size_t)nb * 6);
-  if (kind == 0) {
-#pragma unroll
-    for (int i = 0; i < 36; ++i) out[(size_t)t * 36 + i] = acc[i];
-  } else if (kind == 1) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) out[(size_t)nT * 36 + bi * 6 + i] = acc[i];
+  for (int e = threadIdx.x; e < slots_pad * 36; e += blockDim.x) {
+    const int sl = e / 36, i = e % 36;
+    const int gs = blockIdx.y * slots_pad + sl;
+    if (gs >= nT + nb) continue;
+    double v = 0.0;
+    for (int g = 0; g < KG; ++g) v += red[((size_t)g * slots_pad + sl) * 36 + i];
+    if (gs < nT) out[(size_t)gs * 36 + i] = v;
+    else if (i < 6) out[(size_t)nT * 36 + (gs - nT) * 6 + i] = v;
   }
 }
 
-static void syrk_config(const mcba_handle* h, int& threads, int& gy, int& FB, size_t& smem) {
-  const int nc = h->L.nc, nb = nc / 6, nT = nb * (nb + 1) / 2, total = nT + nb;
-  gy = (total + 287) / 288;
-  threads = (((total + gy - 1) / gy) + 31) / 32 * 32;
-  FB = nc <= 96 ? 32 : (nc <= 192 ? 12 : 4);
-  smem = sizeof(double) * ((size_t)FB * 6 * nc + (size_t)FB * 6);
+struct SyrkConfig {
+  int threads, gy, FB, slots_pad, KG;
+  size_t smem;
+};
+
+static SyrkConfig syrk_config(int nc) {
+  SyrkConfig c;
+  const int nb = nc / 6, nT = nb * (nb + 1) / 2, slots = nT + nb;
+  c.gy = (slots + 287) / 288;
+  c.slots_pad = (((slots + c.gy - 1) / c.gy) + 31) / 32 * 32;
+  c.KG = 384 / c.slots_pad;
+  if (c.KG < 1) c.KG = 1;
+  c.threads = c.slots_pad * c.KG;
+  c.FB = nc <= 96 ? 16 : (nc <= 192 ? 8 : 4);
+  const size_t stage = sizeof(double) * ((size_t)c.FB * 6 * nc + (size_t)c.FB * 6);
+  const size_t red = sizeof(double) * (size_t)c.KG * c.slots_pad * 36;
+  c.smem = kSyrkStages * stage > red ? kSyrkStages * stage : red;
+  return c;
+}
+
+int syrk_grid(int nc, long long F, int n_sm) {
+  const SyrkConfig c = syrk_config(nc);
+  long long g = (F + c.FB - 1) / c.FB;
+  return (int)(g < n_sm ? g : n_sm);
 }
 
 int launch_k2_syrk(mcba_handle* h) {
   const Layout& L = h->L;
-  int threads, gy, FB;
-  size_t smem;
-  syrk_config(h, threads, gy, FB, smem);
+  const SyrkConfig c = syrk_config(L.nc);
   const int nb = L.nc / 6, nT = nb * (nb + 1) / 2;
   const int gx = h->grid_syrk;
-  const long long fpc = (L.F + gx - 1) / gx;
-  MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k2_syrk_kernel<<<dim3(gx, gy), threads, smem, h->stream>>>(h->d_Z, h->d_y, L.nc, nb, nT, L.F, FB, fpc,
-                                                            h->d_partSyrk);
+  long long fpc = (L.F + gx - 1) / gx;
+  fpc = (fpc + c.FB - 1) / c.FB * c.FB;   // whole chunks per CTA keep every TMA source 16-byte aligned
+  MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  k2_syrk_kernel<<<dim3(gx, c.gy), c.threads, c.smem, h->stream>>>(h->d_Z, h->d_y, L.nc, nb, nT, L.F, c.FB,
+                                                                  c.slots_pad, c.KG, fpc, h->d_partSyrk);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
@@ -343,7 +421,7 @@ __global__ void __launch_bounds__(192) backsub_kernel(const BackParams p) {
         s0 = fma(z.x, draw[2 * r], s0);
         s1 = fma(z.y, draw[2 * r + 1], s1);
       }
-      v = p.y[(size_t)tile * 6 * kTile + k * kTile + fl] + (s0 + s1);
+      v = p.y[(size_t)f * 6 + k] + (s0 + s1);
     }
     sv[tid] = v;
     __syncthreads();

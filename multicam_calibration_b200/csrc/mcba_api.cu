@@ -121,6 +121,7 @@ void mcba_default_options(mcba_options* o) {
   o->loss = MCBA_LOSS_SOFT_L1;
   o->f_scale = 1.0;
   o->verbose = 2;
+  o->hessian = MCBA_HESSIAN_AUTO;
   o->lambda0 = 1e-3;
   o->lambda_min = 1e-12;
   o->lambda_max = 1e12;
@@ -155,8 +156,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   h->n_sm = prop.multiProcessorCount;
   MCBA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->grid_frames = (int)std::min<long long>(L.nTiles, h->n_sm);
-  const int FB = L.nc <= 96 ? 32 : (L.nc <= 192 ? 12 : 4);
-  h->grid_syrk = (int)std::min<long long>((F + FB - 1) / FB, 2LL * h->n_sm);
+  h->grid_syrk = syrk_grid(L.nc, F, h->n_sm);
   h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
   h->grid_back = (int)std::min<long long>(L.nTiles, 8LL * h->n_sm);
   const long long n = L.nc + 6 * F;
@@ -382,7 +382,11 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
 
   double lambda = opt.lambda0, nu = 2.0;
   EvalOut ev;
-  if ((rc = evaluate(h, x, lambda, opt.loss, opt.f_scale))) return rc;
+  // Gauss-Newton weights: IRLS far from the minimum, scipy's Triggs scaling once the cost
+  // changes by less than 1 % per step (MCBA_HESSIAN_AUTO); both share gradient and fixed point.
+  bool irls = opt.hessian != MCBA_HESSIAN_TRIGGS && (opt.loss & 0xff) != MCBA_LOSS_LINEAR;
+  auto loss_code = [&]() { return (opt.loss & 0xff) | (irls ? MCBA_LOSS_IRLS : 0); };
+  if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;
   if ((rc = read_eval(h, &ev))) return rc;
   int nfev = 1, njev = 1, iter = 0, status = -2;
   if (!std::isfinite(ev.cost) || !std::isfinite(ev.gnorm)) {
@@ -427,10 +431,11 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       std::swap(x, xt);
       step_norm = sn;
       const double t = 2.0 * ratio - 1.0;
-      lambda = std::max(opt.lambda_min, lambda * std::max(1.0 / 3.0, 1.0 - t * t * t));
+      lambda = std::max(opt.lambda_min, lambda * std::max(0.1, 1.0 - t * t * t));
       nu = 2.0;
       ++iter;
-      if ((rc = evaluate(h, x, lambda, opt.loss, opt.f_scale))) return rc;
+      if (irls && opt.hessian == MCBA_HESSIAN_AUTO && actual < 1e-2 * cost) irls = false;
+      if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;
       if ((rc = read_eval(h, &ev))) return rc;
       ++njev;
       const double cost_prev = cost;
@@ -443,7 +448,7 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       lambda *= nu;
       nu *= 2.0;
       if (lambda > opt.lambda_max) { status = -1; set_error("damping exceeded lambda_max without finding a descent step"); break; }
-      if ((rc = evaluate(h, x, lambda, opt.loss, opt.f_scale))) return rc;   // pose damping is baked into Z
+      if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;   // pose damping is baked into Z
       if ((rc = read_eval(h, &ev))) return rc;
     }
   }

@@ -45,7 +45,7 @@ struct K2Params {
   double inv_c, c2;
   double* Z;       // [f][k][12C]
   double* Linv;    // [tile][21][32]
-  double* y;       // [tile][6][32]
+  double* y;       // [f][6]
   double* gpose;   // [f][6]
   double* D2pose;  // [tile][6][32] running max of diag(V_f)
   double* partU;   // [grid][C][kUPad]
@@ -125,6 +125,7 @@ int launch_predict(mcba_handle* h, const double* x, double* uv_out);
 int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, double* out_scal);
 int launch_k2_frames(mcba_handle* h, const double* x, double lambda, int loss, double f_scale);
 int launch_k2_syrk(mcba_handle* h);
+int syrk_grid(int nc, long long F, int n_sm);
 int launch_finalize(mcba_handle* h);
 int launch_jacobian_blocks(mcba_handle* h, const double* x, double* Jc, double* Jp);
 int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda);

@@ -104,11 +104,17 @@ __device__ __forceinline__ void mat3_vec(const double A[9], const double v[3], d
 // normal equations need:  wg = rho'  (gradient  J^T (rho' f)),
 // wh = max(rho' + 2 rho'' z, EPS)  (Gauss-Newton  J^T diag(wh) J).
 // soft_l1: rho' = (1+z)^-1/2 and rho' + 2 rho'' z = (1+z)^-3/2 exactly.
-enum Loss : int { kLossLinear = 0, kLossSoftL1 = 1 };
+//
+// kLossIrls (bit 8 of the loss code) selects the majorising Gauss-Newton weight
+// wh = rho' instead (iteratively re-weighted least squares): same gradient, cost
+// and stationary points, but a Hessian model that does not collapse when the
+// residuals are still large (rho' + 2 rho'' z -> z^-3/2), which is what makes
+// scipy's Triggs-scaled model crawl far from the minimum.
+enum Loss : int { kLossLinear = 0, kLossSoftL1 = 1, kLossIrls = 0x100 };
 
 __device__ __forceinline__ void robust_weights(int loss, double f, double inv_c, double c2,
                                                double& rho, double& wg, double& wh) {
-  if (loss == kLossLinear) {
+  if ((loss & 0xff) == kLossLinear) {
     rho = f * f;
     wg = 1.0;
     wh = 1.0;
@@ -119,7 +125,7 @@ __device__ __forceinline__ void robust_weights(int loss, double f, double inv_c,
   const double b = rsqrt(t);
   rho = 2.0 * (t * b - 1.0) * c2;
   wg = b;
-  wh = fmax(b * b * b, 2.220446049250313e-16);
+  wh = (loss & kLossIrls) ? b : fmax(b * b * b, 2.220446049250313e-16);
 }
 
 }  // namespace mcba

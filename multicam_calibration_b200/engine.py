@@ -62,8 +62,8 @@ def parse_options(opt_kwargs, n_params):
     if kw.pop("x_scale") != "jac":
         raise ValueError("bundle_adjust: only x_scale='jac' is supported")
     loss = kw.pop("loss")
-    if loss not in _native.LOSSES:
-        raise ValueError(f"bundle_adjust: loss must be one of {sorted(_native.LOSSES)}")
+    if loss not in ("linear", "soft_l1"):
+        raise ValueError("bundle_adjust: loss must be 'soft_l1' or 'linear'")
     o = Options()
     _native.load().mcba_default_options(ctypes.byref(o))
     tol = lambda v: 0.0 if v is None else float(v)
@@ -73,6 +73,10 @@ def parse_options(opt_kwargs, n_params):
     o.loss = _native.LOSSES[loss]
     o.f_scale = float(kw.pop("f_scale", 1.0))
     o.verbose = int(kw.pop("verbose"))
+    hessian = kw.pop("hessian", "auto")
+    if hessian not in _native.HESSIANS:
+        raise ValueError(f"bundle_adjust: hessian must be one of {sorted(_native.HESSIANS)}")
+    o.hessian = _native.HESSIANS[hessian]
     for name in ("lambda0", "lambda_min", "lambda_max"):
         if name in kw:
             setattr(o, name, float(kw.pop(name)))

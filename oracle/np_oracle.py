@@ -387,20 +387,23 @@ def loss_rho(f, loss="soft_l1", f_scale=1.0):
     return (2 * (t ** 0.5 - 1)) * f_scale ** 2, t ** -0.5, (-0.5 * t ** -1.5) / f_scale ** 2
 
 
-def robust_scale(J, f, loss="soft_l1", f_scale=1.0):
+def robust_scale(J, f, loss="soft_l1", f_scale=1.0, hessian="triggs"):
     """scipy optimize/_lsq/common.py:720-731: row-scale J and f so that
     ``J~^T J~`` is the Triggs-corrected Gauss-Newton matrix and ``J~^T f~`` the
-    gradient of ``0.5 sum rho``."""
+    gradient of ``0.5 sum rho``.  ``hessian='irls'`` uses the majorising weight
+    ``rho'`` instead (same gradient and cost; the engine's far-from-minimum mode)."""
     rho, r1, r2 = loss_rho(f, loss, f_scale)
-    s = np.sqrt(np.maximum(r1 + 2 * r2 * f ** 2, EPS))
+    w = r1 if hessian == "irls" else np.maximum(r1 + 2 * r2 * f ** 2, EPS)
+    s = np.sqrt(w)
     return J * s[:, None], f * r1 / s, 0.5 * rho.sum()
 
 
-def normal_equations(params, all_calib_uvs, calib_objpoints, loss="soft_l1", f_scale=1.0):
+def normal_equations(params, all_calib_uvs, calib_objpoints, loss="soft_l1", f_scale=1.0,
+                     hessian="triggs"):
     """Dense ``H = J~^T J~`` (n,n), ``g = J~^T f~`` (n,), cost -- small problems."""
     f = residuals(params, all_calib_uvs, calib_objpoints)
     J = dense_residual_jacobian(params, all_calib_uvs, calib_objpoints)
-    Js, fs, cost = robust_scale(J, f, loss, f_scale)
+    Js, fs, cost = robust_scale(J, f, loss, f_scale, hessian)
     return Js.T @ Js, Js.T @ fs, cost
 
 
@@ -475,3 +478,77 @@ def relative_camera_transforms(all_extrinsics):
     """``T_c T_0^-1`` (C,4,4): invariant to the global rigid gauge."""
     T = transformation_matrix(np.asarray(all_extrinsics, dtype=float))
     return T @ np.linalg.inv(T[0])
+
+
+# --------------------------------------------------------------------------
+# dense restatement of the device Levenberg-Marquardt loop (small problems)
+# --------------------------------------------------------------------------
+def lm_solve(x0, all_calib_uvs, calib_objpoints, ftol=1e-4, xtol=1e-8, gtol=1e-8, max_nfev=None,
+             loss="soft_l1", f_scale=1.0, lambda0=1e-3, lambda_min=1e-12, lambda_max=1e12, trace=None,
+             hessian="auto"):
+    """Mirror of ``mcba_lm_run`` (csrc/mcba_api.cu) with dense numpy algebra:
+    Gauss-Newton weights IRLS -> Triggs once a step changes the cost by < 1 %
+    (``hessian='auto'``), Marquardt scaling D^2 = running max of diag(J~^T J~), Nielsen damping update,
+    gain ratio from ``pred = -0.5 g.d + 0.5 lam d^T D^2 d`` and scipy's termination
+    tests (optimize/_lsq/common.py:705-717).  Returns (x, info dict)."""
+    C = all_calib_uvs.shape[0]
+    x = np.asarray(x0, dtype=float).copy()
+    max_nfev = 100 * x.size if max_nfev is None else max_nfev
+    irls = hessian != "triggs" and loss != "linear"
+    mode = lambda: "irls" if irls else "triggs"
+    H, g, cost = normal_equations(x, all_calib_uvs, calib_objpoints, loss, f_scale, mode())
+    D2 = np.diag(H).copy()
+    lam, nu, nfev, njev, it, status = lambda0, 2.0, 1, 1, 0, None
+    if np.abs(g).max() < gtol:
+        status = 1
+    while status is None:
+        if nfev >= max_nfev:
+            status = 0
+            break
+        D2e = np.where(D2 == 0, 1.0, D2)
+        try:
+            step = lm_step(H, g, C, lam, D2e)
+            ok = np.isfinite(step).all()
+        except np.linalg.LinAlgError:
+            ok = False
+        nfev += 1
+        if ok:
+            cost_new = robust_cost(x + step, all_calib_uvs, calib_objpoints, loss, f_scale)
+            pred = -0.5 * g @ step + 0.5 * lam * step @ (D2e * step)
+            actual = cost - cost_new
+            ratio = actual / pred if pred > 0 else -1.0
+            sn, xn = np.linalg.norm(step), np.linalg.norm(x)
+            f_ok = actual < ftol * cost and ratio > 0.25
+            x_ok = sn < xtol * (xtol + xn)
+            term = 4 if (f_ok and x_ok) else 2 if f_ok else 3 if x_ok else None
+        else:
+            actual, ratio, term, sn = -1.0, -1.0, None, np.nan
+        if ok and actual > 0:
+            x = x + step
+            lam = max(lambda_min, lam * max(0.1, 1.0 - (2.0 * ratio - 1.0) ** 3))
+            nu = 2.0
+            it += 1
+            if irls and hessian == "auto" and actual < 1e-2 * cost:
+                irls = False
+            H, g, cost = normal_equations(x, all_calib_uvs, calib_objpoints, loss, f_scale, mode())
+            D2 = np.maximum(D2, np.diag(H))
+            njev += 1
+            if trace is not None:
+                trace.append((it, nfev, cost, actual, sn, np.abs(g).max(), lam, ratio))
+            if term is not None:
+                status = term
+            elif np.abs(g).max() < gtol:
+                status = 1
+        else:
+            if term in (3, 4):
+                status = 3
+                break
+            lam *= nu
+            nu *= 2.0
+            if lam > lambda_max:
+                status = -1
+            else:   # the pose damping is part of the factorisation: rebuild at the same point
+                H, g, cost = normal_equations(x, all_calib_uvs, calib_objpoints, loss, f_scale, mode())
+                D2 = np.maximum(D2, np.diag(H))
+    return x, dict(cost=cost, nfev=nfev, njev=njev, iterations=it, status=status,
+                   optimality=float(np.abs(g).max()), grad=g, lam=lam)

@@ -127,7 +127,7 @@ def test_jacobian_blocks_match_oracle_and_reference_fd():
         assert rel(J[:, cols], J2[:, cols]) < 1e-5
 
 
-@pytest.mark.parametrize("loss", ["soft_l1", "linear"])
+@pytest.mark.parametrize("loss", ["soft_l1", "linear", "soft_l1_irls"])
 @pytest.mark.parametrize("lam", [0.0, 1e-2])
 def test_reduced_camera_system_matches_oracle(loss, lam):
     g = load_golden("ba_small")
@@ -135,7 +135,9 @@ def test_reduced_camera_system_matches_oracle(loss, lam):
     C = uvs.shape[0]
     prob = mcc.BAProblem(uvs, obj)
     S, b, gcam, cost = prob.build_reduced(x0, lam=lam, loss=loss)
-    H, grad, cost_o = orc.normal_equations(x0, uvs, obj, loss=loss)
+    hessian = "irls" if loss.endswith("irls") else "triggs"
+    loss = loss.replace("_irls", "")
+    H, grad, cost_o = orc.normal_equations(x0, uvs, obj, loss=loss, hessian=hessian)
     D2 = np.diag(H).copy()
     D2[:12 * C] = 0.0                    # camera damping is added by the solve, not by K2
     S_o, b_o = orc.reduced_camera_system(H, grad, C, lam, D2)
@@ -184,6 +186,21 @@ def test_many_cameras_reduced_system_matches_oracle():
 
 
 # ------------------------------------------------------------------ convergence
+@pytest.mark.parametrize("hessian", ["auto", "triggs", "irls"])
+def test_lm_loop_follows_the_dense_mirror(hessian):
+    """The device LM loop and its dense numpy restatement (oracle.lm_solve) take the same
+    path: same number of accepted steps / evaluations and the same final cost."""
+    sc = make_scene(4, 24, sigma=0.4, p_missing_view=0.2, seed=21)
+    x0 = sc.x0()
+    x, res = mcc.BAProblem(sc.uvs, sc.objpoints).solve(x0, ftol=1e-9, xtol=1e-9, hessian=hessian, verbose=0)
+    xo, info = orc.lm_solve(x0, sc.uvs, sc.objpoints, ftol=1e-9, xtol=1e-9, hessian=hessian)
+    assert res.status == info["status"]
+    assert abs(res.iterations - info["iterations"]) <= 1 and abs(res.nfev - info["nfev"]) <= 1
+    assert res.cost == pytest.approx(info["cost"], rel=1e-9)
+    assert orc.reprojection_rms(x, sc.uvs, sc.objpoints) == pytest.approx(
+        orc.reprojection_rms(xo, sc.uvs, sc.objpoints), abs=1e-7)
+
+
 def gauge_free(x, C):
     cams = x[:12 * C].reshape(C, 12)
     return cams[:, :6].copy(), orc.relative_camera_transforms(cams[:, 6:])
