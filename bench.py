@@ -44,6 +44,15 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    def __new__(cls, index):
+        # NVML in-process (1 ms period) when available: the timed region lasts milliseconds,
+        # shorter than nvidia-smi's start-up; the nvidia-smi loop is the fallback.
+        try:
+            import pynvml  # noqa: F401
+            return object.__new__(NvmlClockSampler)
+        except Exception:
+            return object.__new__(cls)
+
     def __init__(self, index):
         self.proc = None
         try:
@@ -74,6 +83,45 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class NvmlClockSampler(ClockSampler):
+    def __init__(self, index):
+        import threading
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        cuda_visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(cuda_visible.split(",")[index]) if cuda_visible and cuda_visible.split(",")[index].isdigit() else index
+        self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        self.sm, self.reasons, self.stop_flag = [], set(), False
+        self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.dev)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(self.mx),
+                "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml"}
 
 
 # ---------------------------------------------------------------------------------------------

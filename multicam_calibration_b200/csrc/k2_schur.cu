@@ -193,7 +193,7 @@ int launch_k2_syrk(mcba_handle* h) {
 // Block (c, c'), c <= c':  S0_cc' = T_c^T ( [c==c'] U_raw,c - (Z Z^T)_cc' ) T_c'
 // T_c = [[I6,0,0],[0,Jl,0],[0,[t]x Jl,I3]]  (rows raw [intr | m | G], cols true [intr | r | t]).
 struct FinalizeParams {
-  int C, nc, nb, nT, nPartU, nPartSyrk, rank;
+  int C, nc, nb, nT, nPartU, nPartSyrk, nPartScal, rank;
   const CamConst* cams;
   const double* partU;     // [nPartU][C][96]
   const double* partS;     // [nPartU][kRsNum]
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
   const int blk = blockIdx.x;
   if (blk == p.C * p.C) {  // scalars
     double a = 0, b = 0, k = 0, g = 0;
-    for (int i = tid; i < p.nPartU; i += blockDim.x) {
+    for (int i = tid; i < p.nPartScal; i += blockDim.x) {
       const double* s = p.partS + (size_t)i * kRsNum;
       a += s[kRsCost]; b += s[kRsSumSq]; k += s[kRsCount]; g = fmax(g, s[kRsGmaxPose]);
     }
@@ -329,12 +329,48 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
   }
 }
 
+// Deterministic sum over per-CTA partial buffers: out[e] = sum_p part[p][e].
+// 64 elements x 4 partial-groups per CTA, 8 independent loads in flight per thread.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partA, int nPartA, int lenA,
+                                                              const double* __restrict__ partB, int nPartB, int lenB,
+                                                              double* __restrict__ out) {
+  __shared__ double s[4][64];
+  const int el = threadIdx.x & 63, pg = threadIdx.x >> 6;
+  const int e = blockIdx.x * 64 + el;
+  double v = 0.0;
+  if (e < lenA + lenB) {
+    const double* src = e < lenA ? partA + e : partB + (e - lenA);
+    const int np = e < lenA ? nPartA : nPartB;
+    const size_t stride = e < lenA ? (size_t)lenA : (size_t)lenB;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int p = pg;
+    for (; p + 28 < np; p += 32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(p + 4 * u) * stride);
+    }
+    for (; p < np; p += 4) a[0] += __ldcg(src + (size_t)p * stride);
+    v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
+  s[pg][el] = v;
+  __syncthreads();
+  if (pg == 0 && e < lenA + lenB) out[e] = (s[0][el] + s[1][el]) + (s[2][el] + s[3][el]);
+}
+
 int launch_finalize(mcba_handle* h) {
   const Layout& L = h->L;
   FinalizeParams p;
   p.C = L.C; p.nc = L.nc; p.nb = L.nc / 6; p.nT = p.nb * (p.nb + 1) / 2;
-  p.nPartU = h->grid_frames; p.nPartSyrk = h->grid_syrk; p.rank = h->rank;
-  p.cams = h->d_cams; p.partU = h->d_partU; p.partS = h->d_partS; p.partSyrk = h->d_partSyrk;
+  {
+    const int lenA = p.nT * 36 + p.nb * 6, lenB = L.C * kUPad;
+    reduce_partials_kernel<<<(lenA + lenB + 63) / 64, 256, 0, h->stream>>>(h->d_partSyrk, h->grid_syrk, lenA, h->d_partU,
+                                                                      h->grid_frames, lenB, h->d_Sraw);
+    h->launches++;
+    MCBA_CUDA(cudaGetLastError());
+    p.partSyrk = h->d_Sraw;
+    p.partU = h->d_Sraw + lenA;
+  }
+  p.nPartU = 1; p.nPartSyrk = 1; p.nPartScal = h->grid_frames; p.rank = h->rank;
+  p.cams = h->d_cams; p.partS = h->d_partS;
   p.red = h->d_red;
   p.offS = L.offS; p.offB = L.offB; p.offG = L.offG; p.offDiag = L.offDiag; p.offScal = L.offScal; p.offRank = L.offRank;
   finalize_kernel<<<L.C * L.C + 1, 160, 0, h->stream>>>(p);

@@ -179,6 +179,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_ALLOC(h->d_partU, (size_t)h->grid_frames * C * kUPad);
   MCBA_ALLOC(h->d_partS, (size_t)h->grid_frames * kRsNum);
   MCBA_ALLOC(h->d_partSyrk, (size_t)h->grid_syrk * ((size_t)nT * 36 + (size_t)nb * 6));
+  MCBA_ALLOC(h->d_Sraw, (size_t)nT * 36 + (size_t)nb * 6 + (size_t)C * kUPad);
   MCBA_ALLOC(h->d_red, L.redLen);
   MCBA_ALLOC(h->d_Sd, (size_t)L.nc * L.nc);
   MCBA_ALLOC(h->d_dcam, 2 * L.nc);
@@ -211,7 +212,7 @@ int mcba_destroy(mcba_handle* h) {
   if (h->solver) cusolverDnDestroy(h->solver);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
-                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work};
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {
     for (int i = 0; i < 4 * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);
