@@ -86,42 +86,45 @@ class ClockSampler:
 
 
 class NvmlClockSampler(ClockSampler):
+    """Polled from the launching thread while the timed kernels are in flight (no helper
+    thread: a Python thread competing for the GIL would slow the enqueue loop itself)."""
+
     def __init__(self, index):
-        import threading
         import pynvml
         self.nv = pynvml
         pynvml.nvmlInit()
-        cuda_visible = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = int(cuda_visible.split(",")[index]) if cuda_visible and cuda_visible.split(",")[index].isdigit() else index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")
+        phys = int(vis[index]) if index < len(vis) and vis[index].strip().isdigit() else index
         self.dev = pynvml.nvmlDeviceGetHandleByIndex(phys)
-        self.sm, self.reasons, self.stop_flag = [], set(), False
+        self.sm, self.reasons = [], set()
         self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        nv = pynvml
+        self.names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                      getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                      getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                      getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        self.get_reasons = (getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None)
+                            or nv.nvmlDeviceGetCurrentClocksThrottleReasons)
 
-    def _run(self):
-        nv = self.nv
-        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
-        while not self.stop_flag:
-            try:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
-                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-                mask = get(self.dev)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.001)
+    def sample(self):
+        try:
+            self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM))
+            mask = self.get_reasons(self.dev)
+            for bit, name in self.names.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def poll_until(self, event):
+        """Sample until the CUDA event has completed (i.e. during the timed region)."""
+        self.sample()
+        while not event.query():
+            self.sample()
 
     def stop(self):
-        self.stop_flag = True
-        self.thread.join(2)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(self.mx),
-                "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml"}
+                "samples": len(self.sm), "reasons": sorted(self.reasons), "source": "nvml polled during the timed region"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -223,6 +226,8 @@ def run_engine(args):
         for _ in range(args.steps):
             step()
         e1.record(prob.stream)
+        if sampler is not None and hasattr(sampler, "poll_until"):
+            sampler.poll_until(e1)
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
@@ -329,7 +334,7 @@ def run_engine(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES, help="frames per GPU (default: the BASELINE workload)")

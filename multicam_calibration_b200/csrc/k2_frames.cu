@@ -14,6 +14,8 @@
 //   * after a CTA-wide exchange of V'' factors V_f + lambda D_f^2 = L L^T (6x6, per lane),
 //   * writes Z_cf = W_cf L^-T, y_f = L^-1 g_f, L^-1 for the SYRK and back-substitution.
 // Nothing per-observation is written: algorithmic HBM traffic is 16 B/observation.
+#include <cstdlib>
+
 #include "mcba_internal.h"
 #include "mcba_obs.cuh"
 
@@ -407,6 +409,9 @@ int launch_k2_frames(mcba_handle* h, const double* x, double lambda, int loss, d
   p.D2pose = h->d_D2pose;
   p.partU = h->d_partU;
   p.partS = h->d_partS;
+  // C <= 6: warp-specialised producer/consumer kernel (k2_frames_ws.cu); MCBA_K2_LEGACY=1 forces this one
+  static const bool legacy = getenv("MCBA_K2_LEGACY") != nullptr;
+  if (L.C <= 6 && !legacy) return launch_k2_frames_ws(h, p);
   const size_t smem = k2_frames_smem(L.C, L.N, p.nwarps);
   const int grid = h->grid_frames;
   if (p.ngroups == 1) {

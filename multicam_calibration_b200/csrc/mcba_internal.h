@@ -124,6 +124,7 @@ int launch_residuals(mcba_handle* h, const double* x, double* r_out);
 int launch_predict(mcba_handle* h, const double* x, double* uv_out);
 int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, double* out_scal);
 int launch_k2_frames(mcba_handle* h, const double* x, double lambda, int loss, double f_scale);
+int launch_k2_frames_ws(mcba_handle* h, const K2Params& p);
 int launch_k2_syrk(mcba_handle* h);
 int syrk_grid(int nc, long long F, int n_sm);
 int launch_finalize(mcba_handle* h);
