@@ -165,8 +165,8 @@ int mcba_triangulate(int device, void* cuda_stream, const double* d_uvs, int n_c
                      const double* h_dist, double* d_points);
 
 /* Per-kernel device timing of the evaluation pass (CUDA events on the handle's stream).
- * Synchronises, returns in ms_out[3] the summed durations of {K2a frames, K2b SYRK,
- * finalize + all-reduce} over the n evaluations since the last call, resets the
+ * Synchronises, returns in ms_out[4] the summed durations of {K2p corner walk, K2c per-frame
+ * Schur, SYRK, finalize + all-reduce} over the n evaluations since the last call, resets the
  * counters and switches recording on/off. */
 int mcba_profile(mcba_handle* h, int enable, double* ms_out, int* n_out);
 

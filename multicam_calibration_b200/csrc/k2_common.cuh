@@ -9,80 +9,35 @@ __host__ __device__ constexpr int tri12(int i, int j) { return i * 12 - (i * (i 
 __host__ __device__ constexpr int sym12(int i, int j) { return i <= j ? tri12(i, j) : tri12(j, i); }
 __host__ __device__ constexpr int tri6(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }
 __host__ __device__ constexpr int sym6(int i, int j) { return i <= j ? tri6(i, j) : tri6(j, i); }
-constexpr int kQ = 78;  // offset of q inside the 96-value accumulator
-
-template <bool IsU>
-__device__ __forceinline__ void accumulate_row(double (&acc)[kUPad], const double (&a)[10], double wh,
-                                               double gf) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const int I = IsU ? kIdxU[i] : kIdxV[i];
-    const double s = wh * a[i];
-    acc[kQ + I] = fma(gf, a[i], acc[kQ + I]);
-#pragma unroll
-    for (int j = i; j < 10; ++j) {
-      const int J = IsU ? kIdxU[j] : kIdxV[j];
-      acc[tri12(I, J)] = fma(s, a[j], acc[tri12(I, J)]);
-    }
+// Accumulator layout of the raw 12x12 Gauss-Newton block A_cf and q_cf (kAcc = 128 slots, 4
+// blocks of 32 for the lane transpose-reduction); raw column order of mcba_obs.cuh
+// [fx fy cx cy k1 k2 | m (3) | G (3)]:
+//   block 0: entries only the u rows touch (columns fx, cx):  19 of A + 2 of q
+//   block 1: entries only the v rows touch (columns fy, cy):  19 of A + 2 of q
+//   blocks 2-3: entries both rows touch (columns k1, k2, ext): 36 of A + 8 of q
+// The four products fx.fy, fx.cy, cx.fy, cx.cy are structurally zero and have no slot (-1).
+__host__ __device__ constexpr int tri8(int i, int j) { return i * 8 - (i * (i - 1)) / 2 + (j - i); }
+__host__ __device__ constexpr int acc_slot_upper(int I, int J) {   // I <= J
+  const bool Iu = I == 0 || I == 2, Iv = I == 1 || I == 3;
+  const bool Ju = J == 0 || J == 2, Jv = J == 1 || J == 3;
+  if ((Iu && Jv) || (Iv && Ju)) return -1;
+  if (Iu || Iv) {
+    const int base = Iu ? 0 : 32;
+    if (Ju || Jv) return base + (I < 2 ? (J < 2 ? 0 : 1) : 2);   // (f,f) (f,c) (c,c)
+    return base + (I < 2 ? 3 : 11) + (J - 4);
   }
+  return 64 + tri8(I - 4, J - 4);
+}
+__host__ __device__ constexpr int acc_slot(int I, int J) { return I <= J ? acc_slot_upper(I, J) : acc_slot_upper(J, I); }
+__host__ __device__ constexpr int acc_slot_q(int I) {
+  return I == 0 ? 19 : I == 2 ? 20 : I == 1 ? 32 + 19 : I == 3 ? 32 + 20 : 64 + 36 + (I - 4);
 }
 
-// Sum over the 32 lanes of v[Base + l] delivered to lane l (recursive halving:
-// 31 shuffles instead of 32 x 5).
-template <int Base>
-__device__ __forceinline__ double lane_transpose_sum32(const double (&v)[kUPad], int lane) {
-  double w[16];
-  {
-    const bool up = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const double keep = up ? v[Base + 16 + i] : v[Base + i];
-      const double send = up ? v[Base + i] : v[Base + 16 + i];
-      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-#pragma unroll
-  for (int half = 8; half >= 1; half >>= 1) {
-    const bool up = lane & half;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const double keep = up ? w[half + i] : w[i];
-      const double send = up ? w[i] : w[half + i];
-      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-    }
-  }
-  return w[0];
-}
-
-// Walk the N corners of one (camera, frame) pair: A = sum w a a^T, q = -sum rho' f a.
-__device__ __forceinline__ void accumulate_pair(const K2Params& p, const Intr& in, const double (&Rcf)[9],
-                                                const double (&tcf)[3], const double2* __restrict__ ob,
-                                                const double* __restrict__ s_obj, double (&acc)[kUPad],
-                                                double& cost_acc, double& sumsq_acc, double& cnt_acc) {
-  const int N = p.N;
-  double2 o = ob[0];
-  for (int n = 0; n < N; ++n) {
-    const double2 cur = o;
-    if (n + 1 < N) o = ob[(size_t)(n + 1) * kTile];
-    const bool hu = cur.x == cur.x, hv = cur.y == cur.y;
-    if (hu | hv) {
-      double pu, pv, au[10], av[10];
-      project_jac(in, Rcf, tcf, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], pu, pv, au, av);
-      const double fu = hu ? cur.x - pu : 0.0, fv = hv ? cur.y - pv : 0.0;
-      double rho, wg, wh;
-      robust_weights(p.loss, fu, p.inv_c, p.c2, rho, wg, wh);
-      if (!hu) wh = 0.0;
-      cost_acc += hu ? rho : 0.0;
-      accumulate_row<true>(acc, au, wh, -wg * fu);
-      robust_weights(p.loss, fv, p.inv_c, p.c2, rho, wg, wh);
-      if (!hv) wh = 0.0;
-      cost_acc += hv ? rho : 0.0;
-      accumulate_row<false>(acc, av, wh, -wg * fv);
-      sumsq_acc += fma(fu, fu, fv * fv);
-      cnt_acc += (hu ? 1.0 : 0.0) + (hv ? 1.0 : 0.0);
-    }
-  }
-}
+// Hand-off from K2p to K2c, per (camera, frame) pair: 63 doubles, [tile][c][63][lane]
+//   0..35  A[i, ext j]  (i = raw intrinsic row 0..5, j = 0..5 over [m | G])
+//   36..56 A[ext r, ext s], r <= s, packed upper (tri6)
+//   57..62 q[ext r]
+constexpr int kHandoff = 63;
 
 // V = P'^T V'' P', g = P'^T g'' with P' = blkdiag(J_l(rho), I); damping lambda * D_f^2 with the
 // running Marquardt scaling; 6x6 Cholesky; returns L^-1 (packed lower) and y = L^-1 g.

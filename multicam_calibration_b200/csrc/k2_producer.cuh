@@ -1,0 +1,328 @@
+// K2p: the per-observation half of the fused residual + analytic Jacobian + Schur pass
+// (replaces scipy's finite-difference Jacobian, bundle_adjustment.py:299-313 /
+// scipy _numdiff.py:288; math in SURVEY.md Appendix A and mcba_math.cuh).
+//
+// Work unit = (camera c, tile of 32 consecutive frames); lane = frame.  A lane owns one
+// (camera, frame) pair, walks its N board corners with coalesced 16-byte loads of the tiled
+// observation SoA ([tile][camera][corner][lane]) and accumulates the raw 12x12 Gauss-Newton
+// block  A_cf = sum_n w a a^T,  q_cf = -sum_n rho' f a  in registers (86 live accumulators,
+// layout in k2_common.cuh).  At the end of the unit
+//   * the full block is added to the camera's U / gradient partial sums (register
+//     transpose-reduction: 4 values per lane, then a fixed-order sum over the CTA's warps),
+//   * the extrinsic part (A[:,ext], A_ext,ext, q_ext: 63 doubles per pair) is handed to the
+//     per-frame Schur kernel K2c through the coalesced hand-off buffer H[tile][c][63][lane].
+// Nothing per-observation is written: algorithmic HBM traffic is 16 B/observation.
+//
+// Scheduling: units are ordered camera-major in groups of kWarps tiles; every CTA owns a
+// contiguous range of groups, so the camera index is CTA-uniform and changes at most a few times
+// per CTA.  All kWarps warps of the CTA walk corners (no consumer warps, no named barriers: the
+// per-frame Schur step is the separate kernel K2c).  The corner loop is ONE branch-free basic
+// block: missing observations are handled with selects, the reciprocal and rsqrt are inlined
+// Newton iterations on MUFU seeds (no slow-path calls), the loss is a template parameter.
+// Measured on B200 (scripts/ubench/k2p_variants.cu, 6 x 50k x 35, 20 % missing views): 0.232 ms,
+// ~61 % of the FP64 pipe; walking u and v rows separately with half the accumulators live (to
+// free registers for software pipelining) was 20 % slower and is not kept.
+#pragma once
+#include "k2_common.cuh"
+
+namespace mcba {
+
+struct K2PParams {
+  int C, N;
+  long long F, nTiles;
+  long long nGroups;          // C * ceil(nTiles / kWarps)
+  const double2* obs;         // tiled [tile][c][n][lane]
+  const double* obj;          // (N,3)
+  const double* x;            // 12C + 6F
+  const CamConst* cams;       // per-camera constants (prep_cameras_kernel)
+  double inv_c, c2;           // 1/f_scale, f_scale^2
+  double* H;                  // [tile][c][63][32]
+  double* partU;              // [grid][C][kAcc]
+  double* partS;              // [grid][kRsNum]
+};
+
+template <bool IsU>
+__device__ __forceinline__ void accumulate_row(double (&acc)[kAcc], const double (&a)[10], double wh, double gf) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int I = IsU ? kIdxU[i] : kIdxV[i];
+    const double s = wh * a[i];
+    acc[acc_slot_q(I)] = fma(gf, a[i], acc[acc_slot_q(I)]);
+#pragma unroll
+    for (int j = i; j < 10; ++j) {
+      const int J = IsU ? kIdxU[j] : kIdxV[j];
+      acc[acc_slot(I, J)] = fma(s, a[j], acc[acc_slot(I, J)]);
+    }
+  }
+}
+
+// Sum over the 32 lanes of v[Base + l] delivered to lane l (recursive halving: 31 shuffles
+// instead of 32 x 5).
+template <int Base>
+__device__ __forceinline__ double lane_transpose_sum32(const double (&v)[kAcc], int lane) {
+  double w[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const double keep = up ? v[Base + 16 + i] : v[Base + i];
+      const double send = up ? v[Base + i] : v[Base + 16 + i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const bool up = lane & half;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double keep = up ? w[half + i] : w[i];
+      const double send = up ? w[i] : w[half + i];
+      w[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return w[0];
+}
+
+// 1/z for finite z of either sign in the normal range: MUFU.RCP64H seed (20 bits) and the same
+// cubic + quadratic Newton sequence CUDA's own 1.0/z uses, without its special-case branch.
+__device__ __forceinline__ double fast_rcp(double z) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z));
+  double e = fma(-z, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  e = fma(-z, y, 1.0);
+  return fma(y, e, y);
+}
+
+// 1/sqrt(t) for t >= 1: MUFU.RSQ64H seed, one cubic and one quadratic correction.
+__device__ __forceinline__ double fast_rsqrt(double t) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
+  double e = fma(-t, y * y, 1.0);
+  y = fma(y * e, fma(0.375, e, 0.5), y);
+  e = fma(-t, y * y, 1.0);
+  return fma(0.5 * y, e, y);
+}
+
+// Robust weights of one scalar residual (see robust_weights in mcba_math.cuh), branch-free on
+// the data: f == 0 for a missing scalar gives rho = 0 and a zero gradient term by itself; only
+// the Gauss-Newton weight needs the validity select.
+template <int kLoss>
+__device__ __forceinline__ void robust_weights_t(double f, bool valid, double inv_c, double c2, double& rho,
+                                                 double& wg, double& wh) {
+  if ((kLoss & 0xff) == kLossLinear) {
+    rho = f * f;
+    wg = 1.0;
+    wh = valid ? 1.0 : 0.0;
+  } else {
+    const double fs = f * inv_c;
+    const double t = fma(fs, fs, 1.0);
+    const double b = fast_rsqrt(t);
+    rho = 2.0 * fma(t, b, -1.0) * c2;
+    wg = b;
+    const double w3 = (kLoss & kLossIrls) ? b : fmax(b * b * b, 2.220446049250313e-16);
+    wh = valid ? w3 : 0.0;
+  }
+}
+
+// Shared part of the projection of one corner: camera-frame point, distortion, d(u,v)/d(x,y).
+struct Proj {
+  double x, y, iz, r2, d, A00, A01, A10, A11, su, sv, pu, pv;
+};
+
+__device__ __forceinline__ void project_shared(const CamConst& cam, const double* __restrict__ sR, double qx,
+                                               double qy, double qz, Proj& o) {
+  // sR: this lane's [Rcf (9) | tcf (3)], stride 32 doubles between entries
+  const double X = fma(sR[0 * 32], qx, fma(sR[1 * 32], qy, fma(sR[2 * 32], qz, sR[9 * 32])));
+  const double Y = fma(sR[3 * 32], qx, fma(sR[4 * 32], qy, fma(sR[5 * 32], qz, sR[10 * 32])));
+  const double Z = fma(sR[6 * 32], qx, fma(sR[7 * 32], qy, fma(sR[8 * 32], qz, sR[11 * 32])));
+  o.iz = fast_rcp(Z);
+  o.x = X * o.iz;
+  o.y = Y * o.iz;
+  o.r2 = fma(o.x, o.x, o.y * o.y);
+  o.d = fma(o.r2, fma(cam.k2, o.r2, cam.k1), 1.0);
+  const double dp = fma(2.0 * cam.k2, o.r2, cam.k1);
+  o.pu = fma(cam.fx, o.x * o.d, cam.cx);
+  o.pv = fma(cam.fy, o.y * o.d, cam.cy);
+  const double xy2 = 2.0 * o.x * o.y * dp;
+  o.A00 = cam.fx * fma(2.0 * o.x * o.x, dp, o.d);
+  o.A01 = cam.fx * xy2;
+  o.A10 = cam.fy * xy2;
+  o.A11 = cam.fy * fma(2.0 * o.y * o.y, dp, o.d);
+  o.su = fma(o.A00, o.x, o.A01 * o.y);
+  o.sv = fma(o.A10, o.x, o.A11 * o.y);
+}
+
+// Raw Jacobian row of u (kU) or v: [d/df, d/dc = 1, d/dk1, d/dk2, m (3), G (3)]  (mcba_obs.cuh).
+template <bool kU>
+__device__ __forceinline__ void jac_row(const CamConst& cam, const Proj& p, double (&a)[10]) {
+  const double f = kU ? cam.fx : cam.fy, w = kU ? p.x : p.y;
+  const double Aa = kU ? p.A00 : p.A10, Ab = kU ? p.A01 : p.A11, s = kU ? p.su : p.sv;
+  a[0] = w * p.d;
+  a[1] = 1.0;
+  a[2] = f * w * p.r2;
+  a[3] = a[2] * p.r2;
+  a[4] = -fma(p.y, s, Ab);
+  a[5] = fma(p.x, s, Aa);
+  a[6] = fma(p.x, Ab, -p.y * Aa);
+  a[7] = Aa * p.iz;
+  a[8] = Ab * p.iz;
+  a[9] = -s * p.iz;
+}
+
+// One unit (camera, 32 frames): walk the N corners, both rows of each observation.
+template <int kLoss>
+__device__ __forceinline__ void walk_corners(const K2PParams& p, const CamConst& cam, const double* __restrict__ sR,
+                                             const double2* __restrict__ ob, const double* __restrict__ s_obj,
+                                             double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
+                                             double& cnt_acc) {
+  const int N = p.N;
+  double2 o0 = ob[0];
+  double2 o1 = N > 1 ? ob[kTile] : o0;
+#pragma unroll 1
+  for (int n = 0; n < N; ++n) {
+    const double2 cur = o0;
+    o0 = o1;
+    if (n + 2 < N) o1 = ob[(size_t)(n + 2) * kTile];
+    Proj pr;
+    project_shared(cam, sR, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], pr);
+    {
+      const bool hu = cur.x == cur.x;
+      const double fu = hu ? cur.x - pr.pu : 0.0;
+      double rho, wg, wh, au[10];
+      robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wh);
+      jac_row<true>(cam, pr, au);
+      cost_acc += rho;
+      sumsq_acc = fma(fu, fu, sumsq_acc);
+      cnt_acc += hu ? 1.0 : 0.0;
+      accumulate_row<true>(acc, au, wh, -wg * fu);
+    }
+    {
+      const bool hv = cur.y == cur.y;
+      const double fv = hv ? cur.y - pr.pv : 0.0;
+      double rho, wg, wh, av[10];
+      robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wh);
+      jac_row<false>(cam, pr, av);
+      cost_acc += rho;
+      sumsq_acc = fma(fv, fv, sumsq_acc);
+      cnt_acc += hv ? 1.0 : 0.0;
+      accumulate_row<false>(acc, av, wh, -wg * fv);
+    }
+  }
+}
+
+template <int kLoss, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = p.C, N = p.N, nc = 12 * C;
+  double* s_obj = smem;                                  // 3N (+pad)
+  double* s_U = s_obj + ((3 * N + 1) & ~1);              // [C][kAcc]   CTA partial sums of U, g
+  double* s_Uw = s_U + (size_t)C * kAcc;                 // [kWarps][kAcc] per-group staging
+  double* s_R = s_Uw + (size_t)kWarps * kAcc;            // [kWarps][12][32] per-lane Rcf | tcf
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_obj[i] = p.obj[i];
+  for (int i = threadIdx.x; i < C * kAcc; i += blockDim.x) s_U[i] = 0.0;
+  double cost_acc = 0.0, sumsq_acc = 0.0, cnt_acc = 0.0;
+  double* sR = s_R + (size_t)warp * 12 * 32 + lane;
+  const long long tileBlocks = (p.nTiles + kWarps - 1) / kWarps;
+  __syncthreads();
+
+  // contiguous range of camera-major groups for this CTA
+  const long long g_begin = (p.nGroups * blockIdx.x) / gridDim.x;
+  const long long g_end = (p.nGroups * (blockIdx.x + 1)) / gridDim.x;
+  for (long long g = g_begin; g < g_end; ++g) {
+    const int c = (int)(g / tileBlocks);                // CTA-uniform
+    const long long tile = (g % tileBlocks) * kWarps + warp;
+    const CamConst& cam = p.cams[c];
+    double* uw = s_Uw + warp * kAcc;
+    if (tile < p.nTiles) {
+      const long long f = tile * kTile + lane;
+      const bool fvalid = f < p.F;
+      {
+        double pose[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
+        double Rp[9], Rcf[9], tcf[3];
+        rodrigues(pose, Rp);
+        mat3_mul(cam.R, Rp, Rcf);
+        mat3_vec(cam.R, pose + 3, tcf);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sR[i * 32] = Rcf[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sR[(9 + i) * 32] = tcf[i] + cam.t[i];
+      }
+      __syncwarp();
+      const double2* ob = p.obs + ((size_t)(tile * C + c) * N) * kTile + lane;
+      double* h = p.H + ((size_t)(tile * C + c) * kHandoff) * kTile + lane;
+      double acc[kAcc];
+#pragma unroll
+      for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+      walk_corners<kLoss>(p, cam, sR, ob, s_obj, acc, cost_acc, sumsq_acc, cnt_acc);
+      uw[lane] = lane_transpose_sum32<0>(acc, lane);
+      uw[32 + lane] = lane_transpose_sum32<32>(acc, lane);
+      uw[64 + lane] = lane_transpose_sum32<64>(acc, lane);
+      uw[96 + lane] = lane_transpose_sum32<96>(acc, lane);
+      // hand-off to K2c: A[int rows, ext], A_ext,ext (upper 21), q_ext
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) h[(size_t)(i * 6 + j) * kTile] = acc[acc_slot(i, 6 + j)];
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int q = r; q < 6; ++q) h[(size_t)(36 + tri6(r, q)) * kTile] = acc[acc_slot(6 + r, 6 + q)];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) h[(size_t)(57 + r) * kTile] = acc[acc_slot_q(6 + r)];
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) uw[32 * b + lane] = 0.0;
+    }
+    // camera block: sum over the CTA's warps in a fixed order
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAcc; i += kWarps * 32) {
+      double s = s_U[c * kAcc + i];
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += s_Uw[w * kAcc + i];
+      s_U[c * kAcc + i] = s;
+    }
+    __syncthreads();
+  }
+
+  // ---------------- CTA epilogue: partial sums ----------------
+  double* pu = p.partU + (size_t)blockIdx.x * C * kAcc;
+  for (int i = threadIdx.x; i < C * kAcc; i += blockDim.x) pu[i] = s_U[i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, off);
+    sumsq_acc += __shfl_xor_sync(0xffffffffu, sumsq_acc, off);
+    cnt_acc += __shfl_xor_sync(0xffffffffu, cnt_acc, off);
+  }
+  __syncthreads();
+  double* s_red = s_Uw;
+  if (lane == 0) {
+    s_red[warp * 4 + 0] = cost_acc;
+    s_red[warp * 4 + 1] = sumsq_acc;
+    s_red[warp * 4 + 2] = cnt_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0, cn = 0;
+    for (int w = 0; w < kWarps; ++w) {
+      a += s_red[w * 4];
+      b += s_red[w * 4 + 1];
+      cn += s_red[w * 4 + 2];
+    }
+    double* ps = p.partS + (size_t)blockIdx.x * kRsNum;
+    ps[kRsCost] = 0.5 * a;
+    ps[kRsSumSq] = b;
+    ps[kRsCount] = cn;
+    ps[kRsGmaxPose] = 0.0;   // pose gradients are K2c's (partG)
+  }
+}
+
+inline size_t k2p_smem(int C, int N, int warps) {
+  return sizeof(double) * (((3 * N + 1) & ~1) + (size_t)C * kAcc + (size_t)warps * kAcc + (size_t)warps * 12 * 32);
+}
+
+}  // namespace mcba

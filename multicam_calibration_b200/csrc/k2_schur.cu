@@ -2,14 +2,11 @@
 // axis), the finalisation of the packed reduced camera system in the true
 // parameter basis, the damped Cholesky solve and K3, the pose back-substitution.
 // Math: SURVEY.md Appendix A ("Schur form for this problem").
-#include "mcba_internal.h"
+#include "k2_common.cuh"
 
 namespace mcba {
 
 __host__ __device__ inline int tile_index(int bi, int bj, int nb) { return bi * nb - (bi * (bi - 1)) / 2 + (bj - bi); }
-__host__ __device__ constexpr int tri12s(int i, int j) {
-  return i <= j ? i * 12 - (i * (i - 1)) / 2 + (j - i) : j * 12 - (j * (j - 1)) / 2 + (i - j);
-}
 
 // ------------------------------------------------------------------ SYRK
 // S_raw = sum_f Z_f Z_f^T (upper block triangle) and sum_f Z_f y_f.
@@ -195,8 +192,10 @@ int launch_k2_syrk(mcba_handle* h) {
 struct FinalizeParams {
   int C, nc, nb, nT, nPartU, nPartSyrk, nPartScal, rank;
   const CamConst* cams;
-  const double* partU;     // [nPartU][C][96]
-  const double* partS;     // [nPartU][kRsNum]
+  const double* partU;     // [nPartU][C][kAcc]
+  const double* partS;     // [nPartScal][kRsNum]  (K2p: cost, sum f^2, count)
+  const double* partG;     // [nPartG] max |pose gradient| per tile (K2c)
+  long long nPartG;
   const double* partSyrk;  // [nPartSyrk][nT*36 + nb*6]
   double* red;
   long long offS, offB, offG, offDiag, offScal, offRank;
@@ -220,8 +219,9 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
     double a = 0, b = 0, k = 0, g = 0;
     for (int i = tid; i < p.nPartScal; i += blockDim.x) {
       const double* s = p.partS + (size_t)i * kRsNum;
-      a += s[kRsCost]; b += s[kRsSumSq]; k += s[kRsCount]; g = fmax(g, s[kRsGmaxPose]);
+      a += s[kRsCost]; b += s[kRsSumSq]; k += s[kRsCount];
     }
+    for (long long i = tid; i < p.nPartG; i += blockDim.x) g = fmax(g, p.partG[i]);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
       a += __shfl_xor_sync(0xffffffffu, a, off);
@@ -266,8 +266,11 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
     for (; k < p.nPartSyrk; ++k) s0 += src[(size_t)k * strideSyrk];
     double s = -((s0 + s1) + (s2 + s3));
     if (c == cp) {
-      const double* us = p.partU + (size_t)c * kUPad + tri12s(i, j);
-      for (int k2 = 0; k2 < p.nPartU; ++k2) uraw += us[(size_t)k2 * p.C * kUPad];
+      const int slot = acc_slot(i, j);   // -1: structurally zero product (fx.fy, fx.cy, cx.fy, cx.cy)
+      if (slot >= 0) {
+        const double* us = p.partU + (size_t)c * kAcc + slot;
+        for (int k2 = 0; k2 < p.nPartU; ++k2) uraw += us[(size_t)k2 * p.C * kAcc];
+      }
       s += uraw;
     }
     M[tid] = s;
@@ -299,8 +302,8 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
   if (tid >= 144 && tid < 156) {
     const int i = tid - 144;
     double graw = 0, zy = 0;
-    const double* gs = p.partU + (size_t)c * kUPad + 78 + i;
-    for (int k = 0; k < p.nPartU; ++k) graw += gs[(size_t)k * p.C * kUPad];
+    const double* gs = p.partU + (size_t)c * kAcc + acc_slot_q(i);
+    for (int k = 0; k < p.nPartU; ++k) graw += gs[(size_t)k * p.C * kAcc];
     const double* zs = p.partSyrk + (size_t)p.nT * 36 + (size_t)(2 * c + i / 6) * 6 + (i % 6);
     for (int k = 0; k < p.nPartSyrk; ++k) zy += zs[(size_t)k * strideSyrk];
     vec[i] = graw;
@@ -361,7 +364,7 @@ int launch_finalize(mcba_handle* h) {
   FinalizeParams p;
   p.C = L.C; p.nc = L.nc; p.nb = L.nc / 6; p.nT = p.nb * (p.nb + 1) / 2;
   {
-    const int lenA = p.nT * 36 + p.nb * 6, lenB = L.C * kUPad;
+    const int lenA = p.nT * 36 + p.nb * 6, lenB = L.C * kAcc;
     reduce_partials_kernel<<<(lenA + lenB + 63) / 64, 256, 0, h->stream>>>(h->d_partSyrk, h->grid_syrk, lenA, h->d_partU,
                                                                       h->grid_frames, lenB, h->d_Sraw);
     h->launches++;
@@ -370,7 +373,7 @@ int launch_finalize(mcba_handle* h) {
     p.partU = h->d_Sraw + lenA;
   }
   p.nPartU = 1; p.nPartSyrk = 1; p.nPartScal = h->grid_frames; p.rank = h->rank;
-  p.cams = h->d_cams; p.partS = h->d_partS;
+  p.cams = h->d_cams; p.partS = h->d_partS; p.partG = h->d_partG; p.nPartG = L.nTiles;
   p.red = h->d_red;
   p.offS = L.offS; p.offB = L.offB; p.offG = L.offG; p.offDiag = L.offDiag; p.offScal = L.offScal; p.offRank = L.offRank;
   finalize_kernel<<<L.C * L.C + 1, 160, 0, h->stream>>>(p);

@@ -66,14 +66,19 @@ struct EvalOut {
 };
 
 // residual + Jacobian + Schur at x; the packed system is left (all-reduced) in d_red
-static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, double f_scale) {
+// (redamp: x and the loss are those of the previous call, only lambda changed -> K2p is skipped)
+static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, double f_scale, bool redamp = false) {
   int rc;
-  const bool prof = h->profile && h->prof_n < kProfRing;
-  cudaEvent_t* ev = prof ? h->prof_ev + 4 * h->prof_n : nullptr;
-  if ((rc = launch_prep_cameras(h, x))) return rc;
+  const bool prof = h->profile && !redamp && h->prof_n < kProfRing;
+  cudaEvent_t* ev = prof ? h->prof_ev + kProfEvents * h->prof_n : nullptr;
+  if ((rc = launch_prep_cameras(h, x))) return rc;   // also after a rejected step: the trial cost pass overwrote d_cams
   if (prof) cudaEventRecord(ev[0], h->stream);
-  if ((rc = launch_k2_frames(h, x, lambda, loss, f_scale))) return rc;
+  if (!redamp) {
+    if ((rc = launch_k2_producer(h, x, loss, f_scale))) return rc;
+  }
   if (prof) cudaEventRecord(ev[1], h->stream);
+  if ((rc = launch_k2_consumer(h, x, lambda))) return rc;
+  if (prof) cudaEventRecord(ev[4], h->stream);
   if ((rc = launch_k2_syrk(h))) return rc;
   if (prof) cudaEventRecord(ev[2], h->stream);
   if ((rc = launch_finalize(h))) return rc;
@@ -155,7 +160,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_CUDA(cudaGetDeviceProperties(&prop, device));
   h->n_sm = prop.multiProcessorCount;
   MCBA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  h->grid_frames = (int)std::min<long long>(L.nTiles, h->n_sm);
+  h->grid_frames = k2_producer_grid(L, h->n_sm, &h->prod_warps);
   h->grid_syrk = syrk_grid(L.nc, F, h->n_sm);
   h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
   h->grid_back = (int)std::min<long long>(L.nTiles, 8LL * h->n_sm);
@@ -176,10 +181,12 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_ALLOC(h->d_gpose, (size_t)L.Fpad * 6);
   MCBA_ALLOC(h->d_D2pose, (size_t)L.nTiles * 6 * kTile);
   MCBA_ALLOC(h->d_D2cam, L.nc);
-  MCBA_ALLOC(h->d_partU, (size_t)h->grid_frames * C * kUPad);
+  MCBA_ALLOC(h->d_H, (size_t)L.nTiles * C * 63 * kTile);
+  MCBA_ALLOC(h->d_partG, L.nTiles);
+  MCBA_ALLOC(h->d_partU, (size_t)h->grid_frames * C * kAcc);
   MCBA_ALLOC(h->d_partS, (size_t)h->grid_frames * kRsNum);
   MCBA_ALLOC(h->d_partSyrk, (size_t)h->grid_syrk * ((size_t)nT * 36 + (size_t)nb * 6));
-  MCBA_ALLOC(h->d_Sraw, (size_t)nT * 36 + (size_t)nb * 6 + (size_t)C * kUPad);
+  MCBA_ALLOC(h->d_Sraw, (size_t)nT * 36 + (size_t)nb * 6 + (size_t)C * kAcc);
   MCBA_ALLOC(h->d_red, L.redLen);
   MCBA_ALLOC(h->d_Sd, (size_t)L.nc * L.nc);
   MCBA_ALLOC(h->d_dcam, 2 * L.nc);
@@ -212,10 +219,10 @@ int mcba_destroy(mcba_handle* h) {
   if (h->solver) cusolverDnDestroy(h->solver);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
-                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw};
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_partG};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {
-    for (int i = 0; i < 4 * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);
+    for (int i = 0; i < kProfEvents * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;
   }
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -449,7 +456,7 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       lambda *= nu;
       nu *= 2.0;
       if (lambda > opt.lambda_max) { status = -1; set_error("damping exceeded lambda_max without finding a descent step"); break; }
-      if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;   // pose damping is baked into Z
+      if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale, true))) return rc;   // pose damping is baked into Z: K2c + SYRK only
       if ((rc = read_eval(h, &ev))) return rc;
     }
   }
@@ -514,21 +521,23 @@ int mcba_profile(mcba_handle* h, int enable, double* ms_out, int* n_out) {
   MCBA_CUDA(cudaSetDevice(h->device));
   MCBA_CUDA(cudaStreamSynchronize(h->stream));
   if (ms_out) {
-    double acc[3] = {0, 0, 0};
+    // events of one evaluation: 0 cameras ready, 1 K2p done, 4 K2c done, 2 SYRK done, 3 finalize + all-reduce done
+    static const int from[4] = {0, 1, 4, 2}, to[4] = {1, 4, 2, 3};
+    double acc[4] = {0, 0, 0, 0};
     for (int i = 0; i < h->prof_n; ++i) {
-      for (int k = 0; k < 3; ++k) {
+      for (int k = 0; k < 4; ++k) {
         float ms = 0;
-        MCBA_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[4 * i + k], h->prof_ev[4 * i + k + 1]));
+        MCBA_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[kProfEvents * i + from[k]], h->prof_ev[kProfEvents * i + to[k]]));
         acc[k] += ms;
       }
     }
-    for (int k = 0; k < 3; ++k) ms_out[k] = acc[k];
+    for (int k = 0; k < 4; ++k) ms_out[k] = acc[k];
   }
   if (n_out) *n_out = h->prof_n;
   h->prof_n = 0;
   if (enable && !h->prof_ev) {
-    h->prof_ev = new cudaEvent_t[4 * kProfRing];
-    for (int i = 0; i < 4 * kProfRing; ++i) MCBA_CUDA(cudaEventCreate(&h->prof_ev[i]));
+    h->prof_ev = new cudaEvent_t[kProfEvents * kProfRing];
+    for (int i = 0; i < kProfEvents * kProfRing; ++i) MCBA_CUDA(cudaEventCreate(&h->prof_ev[i]));
   }
   h->profile = enable != 0;
   return MCBA_OK;

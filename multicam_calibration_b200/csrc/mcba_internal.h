@@ -23,7 +23,8 @@ enum RedScalar : int {
 
 constexpr int kMaxRanks = 64;
 constexpr int kProfRing = 2048;
-constexpr int kUPad = 96;  // 78 (A upper triangle) + 12 (q) padded to 3 x 32
+constexpr int kProfEvents = 5;   // CUDA events recorded per profiled evaluation
+constexpr int kAcc = 128;  // accumulator slots of the raw 12x12 block + q per camera (layout: k2_common.cuh)
 
 struct Layout {
   int C = 0, N = 0;
@@ -31,25 +32,6 @@ struct Layout {
   int nc = 0;  // 12 C
   // packed reduced buffer offsets (doubles)
   long long offS = 0, offB = 0, offG = 0, offDiag = 0, offScal = 0, offRank = 0, redLen = 0;
-};
-
-struct K2Params {
-  int C, N, nwarps, ngroups;
-  long long F, nTiles;
-  const double2* obs;  // tiled [tile][c][n][lane]
-  const double* obj;   // (N,3)
-  const double* x;     // 12C + 6F
-  const CamConst* cams;
-  double lambda;
-  int loss;
-  double inv_c, c2;
-  double* Z;       // [f][k][12C]
-  double* Linv;    // [tile][21][32]
-  double* y;       // [f][6]
-  double* gpose;   // [f][6]
-  double* D2pose;  // [tile][6][32] running max of diag(V_f)
-  double* partU;   // [grid][C][kUPad]
-  double* partS;   // [grid][kRsNum]
 };
 
 }  // namespace mcba
@@ -73,6 +55,8 @@ struct mcba_handle {
   double* d_x = nullptr;
   double* d_xtrial = nullptr;
   mcba::CamConst* d_cams = nullptr;
+  double* d_H = nullptr;      // K2p -> K2c hand-off [tile][c][63][32]
+  double* d_partG = nullptr;  // [nTiles] max |pose gradient| per tile
   double* d_Z = nullptr;
   double* d_Linv = nullptr;
   double* d_y = nullptr;
@@ -88,7 +72,7 @@ struct mcba_handle {
   double* d_dcam = nullptr;   // [delta_cam true (12C) | delta_cam raw (12C)]
   double* d_scal = nullptr;   // step scalars (device), partials
   double* h_pinned = nullptr; // pinned host mirror for small read-backs
-  int grid_frames = 0, grid_syrk = 0, grid_cost = 0, grid_back = 0;
+  int grid_frames = 0, prod_warps = 8, grid_syrk = 0, grid_cost = 0, grid_back = 0;
   // solver
   cusolverDnHandle_t solver = nullptr;
   double* d_work = nullptr;
@@ -100,7 +84,7 @@ struct mcba_handle {
   long long launches = 0;  // kernels launched by this handle (bench gpu_launches)
   // optional per-kernel timing (CUDA events on the launching stream; bench.py roofline)
   bool profile = false;
-  cudaEvent_t* prof_ev = nullptr;   // ring of 4 events per evaluation
+  cudaEvent_t* prof_ev = nullptr;   // ring of kProfEvents events per evaluation
   int prof_n = 0;
 };
 
@@ -123,8 +107,9 @@ int ensure_row_offsets(mcba_handle* h);
 int launch_residuals(mcba_handle* h, const double* x, double* r_out);
 int launch_predict(mcba_handle* h, const double* x, double* uv_out);
 int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, double* out_scal);
-int launch_k2_frames(mcba_handle* h, const double* x, double lambda, int loss, double f_scale);
-int launch_k2_frames_ws(mcba_handle* h, const K2Params& p);
+int launch_k2_producer(mcba_handle* h, const double* x, int loss, double f_scale);
+int launch_k2_consumer(mcba_handle* h, const double* x, double lambda);
+int k2_producer_grid(const mcba::Layout& L, int n_sm, int* warps);
 int launch_k2_syrk(mcba_handle* h);
 int syrk_grid(int nc, long long F, int n_sm);
 int launch_finalize(mcba_handle* h);
