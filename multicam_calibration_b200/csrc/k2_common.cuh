@@ -73,38 +73,49 @@ __device__ __forceinline__ void pose_block_factor(const double (&Vpp)[21], const
     V[7 * i] = fma(lambda, d2, V[7 * i]);
     gmax = fmax(gmax, fabs(gp[i]));
   }
-  double Lm[21];  // Cholesky factor, 1/L_jj stored on the diagonal; empty frames at lambda = 0 give zeros
+  // Cholesky factor, 1/L_jj stored on the diagonal; empty frames at lambda = 0 give zeros.
+  // Every loop has a constant trip count (the triangular bounds are predicates) so that the
+  // whole factorisation unrolls into registers.
+  double Lm[21];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     double s = V[7 * j];
 #pragma unroll
-    for (int k = 0; k < j; ++k) s -= Lm[j * (j + 1) / 2 + k] * Lm[j * (j + 1) / 2 + k];
+    for (int k = 0; k < 6; ++k)
+      if (k < j) s -= Lm[j * (j + 1) / 2 + k] * Lm[j * (j + 1) / 2 + k];
     const double inv = s > 0.0 ? rsqrt(s) : 0.0;
     Lm[j * (j + 1) / 2 + j] = inv;
 #pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double t = V[6 * i + j];
+    for (int i = 0; i < 6; ++i) {
+      if (i > j) {
+        double t = V[6 * i + j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) t -= Lm[i * (i + 1) / 2 + k] * Lm[j * (j + 1) / 2 + k];
-      Lm[i * (i + 1) / 2 + j] = t * inv;
+        for (int k = 0; k < 6; ++k)
+          if (k < j) t -= Lm[i * (i + 1) / 2 + k] * Lm[j * (j + 1) / 2 + k];
+        Lm[i * (i + 1) / 2 + j] = t * inv;
+      }
     }
   }
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     Linv[j * (j + 1) / 2 + j] = Lm[j * (j + 1) / 2 + j];
 #pragma unroll
-    for (int i = j + 1; i < 6; ++i) {
-      double t = 0.0;
+    for (int i = 0; i < 6; ++i) {
+      if (i > j) {
+        double t = 0.0;
 #pragma unroll
-      for (int k = j; k < i; ++k) t += Lm[i * (i + 1) / 2 + k] * Linv[k * (k + 1) / 2 + j];
-      Linv[i * (i + 1) / 2 + j] = -t * Lm[i * (i + 1) / 2 + i];
+        for (int k = 0; k < 6; ++k)
+          if (k >= j && k < i) t += Lm[i * (i + 1) / 2 + k] * Linv[k * (k + 1) / 2 + j];
+        Linv[i * (i + 1) / 2 + j] = -t * Lm[i * (i + 1) / 2 + i];
+      }
     }
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     double t = 0.0;
 #pragma unroll
-    for (int j = 0; j <= i; ++j) t += Linv[i * (i + 1) / 2 + j] * gp[j];
+    for (int j = 0; j < 6; ++j)
+      if (j <= i) t += Linv[i * (i + 1) / 2 + j] * gp[j];
     yv[i] = t;
   }
 }
@@ -122,16 +133,10 @@ __device__ __forceinline__ void z_row(const double (&b)[6], const double (&Jl)[9
   for (int k = 0; k < 6; ++k) {
     double t = 0.0;
 #pragma unroll
-    for (int j = 0; j <= k; ++j) t += w[j] * Linv[k * (k + 1) / 2 + j];
+    for (int j = 0; j < 6; ++j)
+      if (j <= k) t += w[j] * Linv[k * (k + 1) / 2 + j];
     z[k] = t;
   }
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 }  // namespace mcba

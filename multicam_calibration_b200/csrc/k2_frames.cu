@@ -7,8 +7,10 @@
 //       extrinsic part (63 doubles per pair) to K2c.            FP64-pipe bound.
 //   K2c (below)            per frame: map the hand-off to the pose basis (W' = A[:,ext] E',
 //       V'' = E'^T A_ee E'), sum over cameras, factor V_f + lambda D_f^2 = L L^T (6x6, per lane),
-//       write Z_cf = W_cf L^-T, y_f = L^-1 g_f, L^-1 for the SYRK and the back-substitution.
-//       HBM bound (reads 504 B, writes 576 B per pair).
+//       write Z_cf = W_cf L^-T, y_f = L^-1 g_f, L^-1 for the SYRK and the back-substitution,
+//       and the per-tile sums Z y.  Every global access is a coalesced 256-byte row
+//       (lane = frame is the fastest index of H, Z, y, L^-1).  HBM bound: reads 504 B,
+//       writes 576 B per pair.
 //
 // A rejected LM step only changes lambda: K2c is re-run on the same hand-off, K2p is not.
 #include <cstdlib>
@@ -25,9 +27,10 @@ struct K2CParams {
   const double* x;       // 12C + 6F
   const CamConst* cams;
   double lambda;
-  double* Z;             // [f][k][12C]
+  double* Z;             // [tile][row 12C][k 6][lane 32]
   double* Linv;          // [tile][21][32]
-  double* y;             // [f][6]
+  double* y;             // [tile][6][32]
+  double* partZy;        // [tile][12C]  sum over the tile's frames of Z_f y_f
   double* gpose;         // [f][6]
   double* D2pose;        // [tile][6][32] running max of diag(V_f)
   double* partG;         // [tile] max |g_pose|
@@ -131,49 +134,59 @@ __global__ void __launch_bounds__(kW * 32, 2) k2c_kernel(const K2CParams p) {
     double* lo = p.Linv + (size_t)tile * 21 * 32 + lane;
 #pragma unroll
     for (int i = 0; i < 21; ++i) lo[i * 32] = Linv[i];
+    double* yo = p.y + (size_t)tile * 6 * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) yo[i * 32] = yv[i];
     if (fvalid) {
 #pragma unroll
-      for (int i = 0; i < 6; i += 2) {
-        *reinterpret_cast<double2*>(p.y + (size_t)f * 6 + i) = make_double2(yv[i], yv[i + 1]);
+      for (int i = 0; i < 6; i += 2)
         *reinterpret_cast<double2*>(p.gpose + (size_t)f * 6 + i) = make_double2(gp[i], gp[i + 1]);
-      }
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
     if (lane == 0) p.partG[tile] = gmax;
   }
-  // ---- Z_cf = (A[:,ext] E' P') L^-T for this warp's cameras
+  // ---- Z_cf = (A[:,ext] E' P') L^-T for this warp's cameras, one raw camera row at a time
   for (int c = warp; c < C; c += kW) {
     double Rc[9], K[9];
     pose_map(p.cams[c], pose, Rc, K);
     const double* h = p.H + ((size_t)(tile * C + c) * kHandoff) * kTile + lane;
-    double* z = p.Z + (size_t)f * 6 * nc + c * 12;
+    double* z = p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane;
+    double zy[12];
 #pragma unroll
-    for (int i = 0; i < 12; i += 2) {
-      double zr[2][6];
+    for (int row = 0; row < 12; ++row) {
+      double am[3], ag[3];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int row = i + hh;
-        double am[3], ag[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          am[j] = row < 6 ? h[(size_t)(row * 6 + j) * kTile] : h[(size_t)(36 + sym6(row - 6, j)) * kTile];
-          ag[j] = row < 6 ? h[(size_t)(row * 6 + 3 + j) * kTile] : h[(size_t)(36 + sym6(row - 6, 3 + j)) * kTile];
-        }
-        double b[6];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          b[k] = am[0] * Rc[k] + am[1] * Rc[3 + k] + am[2] * Rc[6 + k] + ag[0] * K[k] + ag[1] * K[3 + k] +
-                 ag[2] * K[6 + k];
-          b[3 + k] = ag[0] * Rc[k] + ag[1] * Rc[3 + k] + ag[2] * Rc[6 + k];
-        }
-        z_row(b, Jl, Linv, zr[hh]);
+      for (int j = 0; j < 3; ++j) {
+        am[j] = row < 6 ? h[(size_t)(row * 6 + j) * kTile] : h[(size_t)(36 + sym6(row - 6, j)) * kTile];
+        ag[j] = row < 6 ? h[(size_t)(row * 6 + 3 + j) * kTile] : h[(size_t)(36 + sym6(row - 6, 3 + j)) * kTile];
       }
-      if (fvalid) {
+      double b[6], zr[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k)
-          *reinterpret_cast<double2*>(z + (size_t)k * nc + i) = make_double2(zr[0][k], zr[1][k]);
+      for (int k = 0; k < 3; ++k) {
+        b[k] = am[0] * Rc[k] + am[1] * Rc[3 + k] + am[2] * Rc[6 + k] + ag[0] * K[k] + ag[1] * K[3 + k] +
+               ag[2] * K[6 + k];
+        b[3 + k] = ag[0] * Rc[k] + ag[1] * Rc[3 + k] + ag[2] * Rc[6 + k];
       }
+      z_row(b, Jl, Linv, zr);
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        z[(size_t)(row * 6 + k) * kTile] = zr[k];   // padded lanes carry zeros (their hand-off is zero)
+        t = fma(zr[k], yv[k], t);
+      }
+      zy[row] = t;
+    }
+#pragma unroll
+    for (int row = 0; row < 12; ++row) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) zy[row] += __shfl_xor_sync(0xffffffffu, zy[row], off);
+    }
+    if (lane < 12) {
+      double v = zy[0];
+#pragma unroll
+      for (int row = 1; row < 12; ++row) v = lane == row ? zy[row] : v;
+      p.partZy[(size_t)tile * nc + c * 12 + lane] = v;
     }
   }
 }
@@ -247,6 +260,7 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
   p.gpose = h->d_gpose;
   p.D2pose = h->d_D2pose;
   p.partG = h->d_partG;
+  p.partZy = h->d_partZy;
   const int grid = (int)L.nTiles;
   if (L.C >= 6) k2c_kernel<6><<<grid, 192, 0, h->stream>>>(p);
   else if (L.C >= 3) k2c_kernel<3><<<grid, 96, 0, h->stream>>>(p);

@@ -9,11 +9,16 @@ namespace mcba {
 __host__ __device__ inline int tile_index(int bi, int bj, int nb) { return bi * nb - (bi * (bi - 1)) / 2 + (bj - bi); }
 
 // ------------------------------------------------------------------ SYRK
-// S_raw = sum_f Z_f Z_f^T (upper block triangle) and sum_f Z_f y_f.
-// Slot s < nT owns the 6x6 block (bi <= bj) of S_raw, slots nT .. nT+nb-1 own 6 entries
-// of Z y.  The K axis (frame, pose column) is split over KG thread groups; each
-// persistent CTA streams its contiguous range of Z through a 2-stage shared-memory
-// ring filled by TMA bulk copies (cp.async.bulk + mbarrier) so loads overlap the FMAs.
+// S_raw = sum_f Z_f Z_f^T over this rank's frames, on the FP64 tensor path (DMMA m8n8k4).
+// Z is [tile][row][k*32 + lane]: per tile a row-major (nc x 192) matrix whose K axis is
+// (pose column, frame).  Persistent CTAs stream (tile, K-chunk) stages into shared memory with
+// bulk async copies (one per row, rows padded by 4 doubles so that the 8 x 4 fragment loads are
+// bank-conflict free) through a 3-stage mbarrier ring; each of the 8 warps owns up to NT 8x8
+// tiles of the upper block triangle and keeps their accumulators in registers for the whole
+// kernel.  The A fragment of row block I and the B fragment of row block J are the same
+// mapping (lane -> row I*8 + lane/4, k = k0 + lane%4), so one load serves both roles.
+// B200: DMMA and DFMA share the FP64 pipe at the same FMA rate (profiles/r01_b_ubench_*), but
+// one DMMA replaces 8 DFMA issue slots and all the operand shuffling of a register-tiled SYRK.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -38,149 +43,163 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
-constexpr int kSyrkStages = 2;
+constexpr int kSyrkStages = 3;
+constexpr int kSyrkWarps = 8;
+constexpr int kZK = 6 * kTile;   // K extent of one tile of Z
 
-__global__ void __launch_bounds__(384, 1) k2_syrk_kernel(const double* __restrict__ Z, const double* __restrict__ y,
-                                                         int nc, int nb, int nT, long long F, int FB, int slots_pad,
-                                                         int KG, long long frames_per_cta, double* __restrict__ part) {
+struct SyrkParams {
+  const double* Z;
+  int nc, nc8, nb8, nT;      // rows, rows padded to 8, row blocks, upper-triangle 8x8 tiles
+  long long nTiles;
+  int KW;                    // K width of one stage (divides 192, multiple of 4)
+  double* part;              // [gridDim.x][nc8 * nc8]
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kSyrkWarps * 32, 1) k2_syrk_kernel(const SyrkParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const size_t slab_doubles = (size_t)FB * 6 * nc;
-  const size_t stage_doubles = slab_doubles + (size_t)FB * 6;     // Z slab + y slab
-  double* stages = reinterpret_cast<double*>(smem_raw);
   __shared__ unsigned long long full_bar[kSyrkStages];
+  double* stages = reinterpret_cast<double*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ld = p.KW + 4;
+  const size_t stage_doubles = (size_t)p.nc8 * ld;
 
-  const int slot_local = threadIdx.x % slots_pad, kg = threadIdx.x / slots_pad;
-  const int slot = blockIdx.y * slots_pad + slot_local;
-  int kind = 2, bi = 0, bj = 0;
-  if (slot_local < slots_pad && slot < nT) {
-    kind = 0;
-    int rem = slot;
-    while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
-    bj = bi + rem;
-  } else if (slot < nT + nb) {
-    kind = 1;
-    bi = slot - nT;
-  }
-  double acc[36];
+  // this warp's tiles: NT consecutive tiles of the row-major upper block triangle
+  int offA[NT], offB[NT];
+  bool valid[NT];
+  {
+    const int t0 = ((int)blockIdx.y * kSyrkWarps + warp) * NT;
+    int I = 0, rem = t0;
+    while (I < p.nb8 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
+    int J = I + rem;
 #pragma unroll
-  for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+    for (int s = 0; s < NT; ++s) {
+      valid[s] = t0 + s < p.nT;
+      offA[s] = (I * 8 + (lane >> 2)) * ld + (lane & 3);
+      offB[s] = (J * 8 + (lane >> 2)) * ld + (lane & 3);
+      if (valid[s]) { ++J; if (J == p.nb8) { ++I; J = I; } }
+    }
+  }
+  double acc[NT][2];
+#pragma unroll
+  for (int s = 0; s < NT; ++s) acc[s][0] = acc[s][1] = 0.0;
 
-  const long long f_begin = blockIdx.x * frames_per_cta;
-  long long f_end = f_begin + frames_per_cta;
-  if (f_end > F) f_end = F;
-  const int n_chunks = f_end > f_begin ? (int)((f_end - f_begin + FB - 1) / FB) : 0;
+  const int chunks = kZK / p.KW;
+  const long long my_tiles = p.nTiles > blockIdx.x ? (p.nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long n_units = my_tiles * chunks;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSyrkStages; ++s) mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // padding rows nc .. nc8-1 are never written by the copies: zero them once
+  for (int s = 0; s < kSyrkStages; ++s)
+    for (int i = threadIdx.x; i < (p.nc8 - p.nc) * ld; i += blockDim.x) stages[s * stage_doubles + (size_t)p.nc * ld + i] = 0.0;
   __syncthreads();
-  auto issue = [&](int chunk) {
-    const int s = chunk % kSyrkStages;
-    const long long f0 = f_begin + (long long)chunk * FB;
-    const int nfr = (int)((f_end - f0) < FB ? (f_end - f0) : FB);
+
+  auto issue = [&](long long unit) {   // called by all lanes of warp 0
+    const int s = (int)(unit % kSyrkStages);
+    const long long tile = blockIdx.x + (unit / chunks) * gridDim.x;
+    const int ch = (int)(unit % chunks);
     double* dst = stages + (size_t)s * stage_doubles;
-    const unsigned zb = (unsigned)(nfr * 6 * nc * sizeof(double)), yb = (unsigned)(nfr * 6 * sizeof(double));
-    mbar_expect_tx(&full_bar[s], zb + yb);
-    tma_load_1d(dst, Z + (size_t)f0 * 6 * nc, zb, &full_bar[s]);
-    tma_load_1d(dst + slab_doubles, y + (size_t)f0 * 6, yb, &full_bar[s]);
+    const double* src = p.Z + ((size_t)tile * p.nc) * kZK + (size_t)ch * p.KW;
+    if (lane == 0) mbar_expect_tx(&full_bar[s], (unsigned)(p.nc * p.KW * sizeof(double)));
+    __syncwarp();
+    for (int r = lane; r < p.nc; r += 32)
+      tma_load_1d(dst + (size_t)r * ld, src + (size_t)r * kZK, (unsigned)(p.KW * sizeof(double)), &full_bar[s]);
   };
-  if (threadIdx.x == 0) {
-    for (int c = 0; c < kSyrkStages && c < n_chunks; ++c) issue(c);
+  if (warp == 0) {
+    for (long long u = 0; u < kSyrkStages && u < n_units; ++u) issue(u);
   }
-  for (int chunk = 0; chunk < n_chunks; ++chunk) {
-    const int s = chunk % kSyrkStages;
-    mbar_wait(&full_bar[s], (unsigned)((chunk / kSyrkStages) & 1));
-    const long long f0 = f_begin + (long long)chunk * FB;
-    const int nk = (int)((f_end - f0) < FB ? (f_end - f0) : FB) * 6;
-    const double* slab = stages + (size_t)s * stage_doubles;
-    if (kind == 0) {
-      const double* ra = slab + 6 * bi;
-      const double* rb = slab + 6 * bj;
+  for (long long unit = 0; unit < n_units; ++unit) {
+    const int s = (int)(unit % kSyrkStages);
+    mbar_wait(&full_bar[s], (unsigned)((unit / kSyrkStages) & 1));
+    const double* st = stages + (size_t)s * stage_doubles;
 #pragma unroll 2
-      for (int kk = kg; kk < nk; kk += KG) {
-        const double2 a0 = *reinterpret_cast<const double2*>(ra + (size_t)kk * nc);
-        const double2 a1 = *reinterpret_cast<const double2*>(ra + (size_t)kk * nc + 2);
-        const double2 a2 = *reinterpret_cast<const double2*>(ra + (size_t)kk * nc + 4);
-        const double2 b0 = *reinterpret_cast<const double2*>(rb + (size_t)kk * nc);
-        const double2 b1 = *reinterpret_cast<const double2*>(rb + (size_t)kk * nc + 2);
-        const double2 b2 = *reinterpret_cast<const double2*>(rb + (size_t)kk * nc + 4);
-        const double a[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
-        const double b[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+    for (int k0 = 0; k0 < p.KW; k0 += 4) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j < 6; ++j) acc[i * 6 + j] = fma(a[i], b[j], acc[i * 6 + j]);
-      }
-    } else if (kind == 1) {
-      const double* ra = slab + 6 * bi;
-      const double* ysm = slab + slab_doubles;
-      for (int kk = kg; kk < nk; kk += KG) {
-        const double yk = ysm[kk];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) acc[i] = fma(ra[(size_t)kk * nc + i], yk, acc[i]);
+      for (int sl = 0; sl < NT; ++sl) {
+        if (valid[sl]) {
+          const double a = st[offA[sl] + k0];
+          const double b = st[offB[sl] + k0];
+          dmma_m8n8k4(acc[sl][0], acc[sl][1], a, b);
+        }
       }
     }
     __syncthreads();   // everyone is done with stage s: refill it
-    if (threadIdx.x == 0 && chunk + kSyrkStages < n_chunks) issue(chunk + kSyrkStages);
+    if (warp == 0 && unit + kSyrkStages < n_units) issue(unit + kSyrkStages);
   }
 
-  // reduce the KG partial accumulators through shared memory, then one partial per CTA
-  double* red = stages;   // [KG][slots_pad][36]
-  if (kind != 2) {
+  // one partial per CTA column; tiles of different blockIdx.y are disjoint
+  double* out = p.part + (size_t)blockIdx.x * p.nc8 * p.nc8;
+  {
+    const int t0 = ((int)blockIdx.y * kSyrkWarps + warp) * NT;
+    int I = 0, rem = t0;
+    while (I < p.nb8 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
+    int J = I + rem;
 #pragma unroll
-    for (int i = 0; i < 36; ++i) red[((size_t)kg * slots_pad + slot_local) * 36 + i] = acc[i];
-  }
-  __syncthreads();
-  double* out = part + (size_t)blockIdx.x * ((size_t)nT * 36 + (size_t)nb * 6);
-  for (int e = threadIdx.x; e < slots_pad * 36; e += blockDim.x) {
-    const int sl = e / 36, i = e % 36;
-    const int gs = blockIdx.y * slots_pad + sl;
-    if (gs >= nT + nb) continue;
-    double v = 0.0;
-    for (int g = 0; g < KG; ++g) v += red[((size_t)g * slots_pad + sl) * 36 + i];
-    if (gs < nT) out[(size_t)gs * 36 + i] = v;
-    else if (i < 6) out[(size_t)nT * 36 + (gs - nT) * 6 + i] = v;
+    for (int s = 0; s < NT; ++s) {
+      if (valid[s]) {
+        *reinterpret_cast<double2*>(out + (size_t)(I * 8 + (lane >> 2)) * p.nc8 + J * 8 + 2 * (lane & 3)) =
+            make_double2(acc[s][0], acc[s][1]);
+        ++J;
+        if (J == p.nb8) { ++I; J = I; }
+      }
+    }
   }
 }
 
 struct SyrkConfig {
-  int threads, gy, FB, slots_pad, KG;
+  int NT, gy, KW;
   size_t smem;
 };
 
 static SyrkConfig syrk_config(int nc) {
   SyrkConfig c;
-  const int nb = nc / 6, nT = nb * (nb + 1) / 2, slots = nT + nb;
-  c.gy = (slots + 287) / 288;
-  c.slots_pad = (((slots + c.gy - 1) / c.gy) + 31) / 32 * 32;
-  c.KG = 384 / c.slots_pad;
-  if (c.KG < 1) c.KG = 1;
-  c.threads = c.slots_pad * c.KG;
-  c.FB = nc <= 96 ? 16 : (nc <= 192 ? 8 : 4);
-  const size_t stage = sizeof(double) * ((size_t)c.FB * 6 * nc + (size_t)c.FB * 6);
-  const size_t red = sizeof(double) * (size_t)c.KG * c.slots_pad * 36;
-  c.smem = kSyrkStages * stage > red ? kSyrkStages * stage : red;
+  const int nc8 = (nc + 7) / 8 * 8, nb8 = nc8 / 8, nT = nb8 * (nb8 + 1) / 2;
+  const int per_warp = (nT + kSyrkWarps - 1) / kSyrkWarps;
+  c.NT = per_warp <= 3 ? 3 : (per_warp <= 6 ? 6 : 12);
+  c.gy = (nT + kSyrkWarps * c.NT - 1) / (kSyrkWarps * c.NT);
+  static const int widths[] = {192, 96, 64, 48, 32, 16, 8};
+  c.KW = 8;
+  for (int w : widths) {
+    if ((size_t)kSyrkStages * nc8 * (w + 4) * sizeof(double) <= 200 * 1024) { c.KW = w; break; }
+  }
+  c.smem = (size_t)kSyrkStages * nc8 * (c.KW + 4) * sizeof(double);
   return c;
 }
 
 int syrk_grid(int nc, long long F, int n_sm) {
-  const SyrkConfig c = syrk_config(nc);
-  long long g = (F + c.FB - 1) / c.FB;
-  return (int)(g < n_sm ? g : n_sm);
+  (void)nc;
+  const long long tiles = (F + kTile - 1) / kTile;
+  return (int)(tiles < n_sm ? tiles : n_sm);
 }
 
 int launch_k2_syrk(mcba_handle* h) {
   const Layout& L = h->L;
   const SyrkConfig c = syrk_config(L.nc);
-  const int nb = L.nc / 6, nT = nb * (nb + 1) / 2;
-  const int gx = h->grid_syrk;
-  long long fpc = (L.F + gx - 1) / gx;
-  fpc = (fpc + c.FB - 1) / c.FB * c.FB;   // whole chunks per CTA keep every TMA source 16-byte aligned
-  MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-  k2_syrk_kernel<<<dim3(gx, c.gy), c.threads, c.smem, h->stream>>>(h->d_Z, h->d_y, L.nc, nb, nT, L.F, c.FB,
-                                                                  c.slots_pad, c.KG, fpc, h->d_partSyrk);
+  SyrkParams p;
+  p.Z = h->d_Z;
+  p.nc = L.nc; p.nc8 = L.nc8; p.nb8 = L.nc8 / 8; p.nT = p.nb8 * (p.nb8 + 1) / 2;
+  p.nTiles = L.nTiles;
+  p.KW = c.KW;
+  p.part = h->d_partSyrk;
+  const dim3 grid(h->grid_syrk, c.gy);
+#define MCBA_SYRK_LAUNCH(NTV)                                                                                         \
+  do {                                                                                                                \
+    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));    \
+    k2_syrk_kernel<NTV><<<grid, kSyrkWarps * 32, c.smem, h->stream>>>(p);                                              \
+  } while (0)
+  if (c.NT == 3) MCBA_SYRK_LAUNCH(3);
+  else if (c.NT == 6) MCBA_SYRK_LAUNCH(6);
+  else MCBA_SYRK_LAUNCH(12);
+#undef MCBA_SYRK_LAUNCH
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
@@ -190,13 +209,14 @@ int launch_k2_syrk(mcba_handle* h) {
 // Block (c, c'), c <= c':  S0_cc' = T_c^T ( [c==c'] U_raw,c - (Z Z^T)_cc' ) T_c'
 // T_c = [[I6,0,0],[0,Jl,0],[0,[t]x Jl,I3]]  (rows raw [intr | m | G], cols true [intr | r | t]).
 struct FinalizeParams {
-  int C, nc, nb, nT, nPartU, nPartSyrk, nPartScal, rank;
+  int C, nc, nc8, nPartScal, rank;
   const CamConst* cams;
-  const double* partU;     // [nPartU][C][kAcc]
+  const double* Sraw;      // [nc8][nc8] sum Z Z^T, upper 8x8 block triangle valid (reduced over CTAs)
+  const double* Zy;        // [nc] sum Z y (reduced over tiles)
+  const double* Uraw;      // [C][kAcc] camera blocks / gradients, raw basis (reduced over CTAs)
   const double* partS;     // [nPartScal][kRsNum]  (K2p: cost, sum f^2, count)
   const double* partG;     // [nPartG] max |pose gradient| per tile (K2c)
   long long nPartG;
-  const double* partSyrk;  // [nPartSyrk][nT*36 + nb*6]
   double* red;
   long long offS, offB, offG, offDiag, offScal, offRank;
 };
@@ -244,33 +264,18 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
   }
   const int c = blk / p.C, cp = blk % p.C;
   if (c > cp) return;
-  const size_t strideSyrk = (size_t)p.nT * 36 + (size_t)p.nb * 6;
   build_T(p.cams[c], Tc, tid);
   build_T(p.cams[cp], Tp, tid);
   double uraw = 0.0;
   if (tid < 144) {
     const int i = tid / 12, j = tid % 12;
     const int r = 12 * c + i, q = 12 * cp + j;
-    int bi = r / 6, bj = q / 6, e;
-    if (bi <= bj) e = (r % 6) * 6 + (q % 6);
-    else { const int tmp = bi; bi = bj; bj = tmp; e = (q % 6) * 6 + (r % 6); }
-    const double* src = p.partSyrk + (size_t)tile_index(bi, bj, p.nb) * 36 + e;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int k = 0;
-    for (; k + 4 <= p.nPartSyrk; k += 4) {
-      s0 += src[(size_t)k * strideSyrk];
-      s1 += src[(size_t)(k + 1) * strideSyrk];
-      s2 += src[(size_t)(k + 2) * strideSyrk];
-      s3 += src[(size_t)(k + 3) * strideSyrk];
-    }
-    for (; k < p.nPartSyrk; ++k) s0 += src[(size_t)k * strideSyrk];
-    double s = -((s0 + s1) + (s2 + s3));
+    // r <= q element-wise within a diagonal camera block is not guaranteed: pick the stored 8x8 tile
+    const double zz = (r / 8 <= q / 8) ? p.Sraw[(size_t)r * p.nc8 + q] : p.Sraw[(size_t)q * p.nc8 + r];
+    double s = -zz;
     if (c == cp) {
       const int slot = acc_slot(i, j);   // -1: structurally zero product (fx.fy, fx.cy, cx.fy, cx.cy)
-      if (slot >= 0) {
-        const double* us = p.partU + (size_t)c * kAcc + slot;
-        for (int k2 = 0; k2 < p.nPartU; ++k2) uraw += us[(size_t)k2 * p.C * kAcc];
-      }
+      if (slot >= 0) uraw = p.Uraw[(size_t)c * kAcc + slot];
       s += uraw;
     }
     M[tid] = s;
@@ -301,11 +306,8 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
   if (tid < 144) M[tid] = uraw;
   if (tid >= 144 && tid < 156) {
     const int i = tid - 144;
-    double graw = 0, zy = 0;
-    const double* gs = p.partU + (size_t)c * kAcc + acc_slot_q(i);
-    for (int k = 0; k < p.nPartU; ++k) graw += gs[(size_t)k * p.C * kAcc];
-    const double* zs = p.partSyrk + (size_t)p.nT * 36 + (size_t)(2 * c + i / 6) * 6 + (i % 6);
-    for (int k = 0; k < p.nPartSyrk; ++k) zy += zs[(size_t)k * strideSyrk];
+    const double graw = p.Uraw[(size_t)c * kAcc + acc_slot_q(i)];
+    const double zy = p.Zy[12 * c + i];
     vec[i] = graw;
     vec[12 + i] = graw - zy;
   }
@@ -332,47 +334,66 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
   }
 }
 
-// Deterministic sum over per-CTA partial buffers: out[e] = sum_p part[p][e].
-// 64 elements x 4 partial-groups per CTA, 8 independent loads in flight per thread.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partA, int nPartA, int lenA,
-                                                              const double* __restrict__ partB, int nPartB, int lenB,
-                                                              double* __restrict__ out) {
-  __shared__ double s[4][64];
-  const int el = threadIdx.x & 63, pg = threadIdx.x >> 6;
-  const int e = blockIdx.x * 64 + el;
+// Deterministic sum over partial buffers: out[e] = sum_p part[p][e] for up to two concatenated
+// segments.  kEl elements x kPg partial-groups per 256-thread CTA (wide segments with few
+// partials use 64 x 4, the narrow per-tile Z y sums with thousands of partials 8 x 32), 8
+// independent loads in flight per thread, fixed summation order.
+struct ReduceSeg {
+  const double* part;
+  int n_part, len;
+};
+template <int kEl, int kPg>
+__global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceSeg s0, ReduceSeg s1, double* __restrict__ out) {
+  static_assert(kEl * kPg == 256, "one thread per (element, partial group)");
+  __shared__ double sm[kPg][kEl];
+  const int el = threadIdx.x % kEl, pg = threadIdx.x / kEl;
+  const int e = blockIdx.x * kEl + el;
   double v = 0.0;
-  if (e < lenA + lenB) {
-    const double* src = e < lenA ? partA + e : partB + (e - lenA);
-    const int np = e < lenA ? nPartA : nPartB;
-    const size_t stride = e < lenA ? (size_t)lenA : (size_t)lenB;
+  const int total = s0.len + s1.len;
+  if (e < total) {
+    const ReduceSeg sg = e < s0.len ? s0 : s1;
+    const double* src = sg.part + (e < s0.len ? e : e - s0.len);
+    const int np = sg.n_part;
+    const size_t stride = (size_t)sg.len;
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int p = pg;
-    for (; p + 28 < np; p += 32) {
+    for (; p + 7 * kPg < np; p += 8 * kPg) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(p + 4 * u) * stride);
+      for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(p + kPg * u) * stride);
     }
-    for (; p < np; p += 4) a[0] += __ldcg(src + (size_t)p * stride);
+    for (; p < np; p += kPg) a[0] += __ldcg(src + (size_t)p * stride);
     v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
-  s[pg][el] = v;
+  sm[pg][el] = v;
   __syncthreads();
-  if (pg == 0 && e < lenA + lenB) out[e] = (s[0][el] + s[1][el]) + (s[2][el] + s[3][el]);
+  if (pg == 0 && e < total) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < kPg; ++g) t += sm[g][el];
+    out[e] = t;
+  }
 }
 
 int launch_finalize(mcba_handle* h) {
   const Layout& L = h->L;
   FinalizeParams p;
-  p.C = L.C; p.nc = L.nc; p.nb = L.nc / 6; p.nT = p.nb * (p.nb + 1) / 2;
+  p.C = L.C; p.nc = L.nc; p.nc8 = L.nc8;
+  const int lenS = L.nc8 * L.nc8, lenZy = L.nc, lenU = L.C * kAcc;
   {
-    const int lenA = p.nT * 36 + p.nb * 6, lenB = L.C * kAcc;
-    reduce_partials_kernel<<<(lenA + lenB + 63) / 64, 256, 0, h->stream>>>(h->d_partSyrk, h->grid_syrk, lenA, h->d_partU,
-                                                                      h->grid_frames, lenB, h->d_Sraw);
-    h->launches++;
+    // d_Sraw = [S (nc8^2) | U (C kAcc) | Z y (nc)]
+    const ReduceSeg s0{h->d_partSyrk, h->grid_syrk, lenS};
+    const ReduceSeg s1{h->d_partU, h->grid_frames, lenU};
+    reduce_partials_kernel<64, 4><<<(lenS + lenU + 63) / 64, 256, 0, h->stream>>>(s0, s1, h->d_Sraw);
+    const ReduceSeg z0{h->d_partZy, (int)L.nTiles, lenZy};
+    const ReduceSeg z1{nullptr, 0, 0};
+    reduce_partials_kernel<8, 32><<<(lenZy + 7) / 8, 256, 0, h->stream>>>(z0, z1, h->d_Sraw + lenS + lenU);
+    h->launches += 2;
     MCBA_CUDA(cudaGetLastError());
-    p.partSyrk = h->d_Sraw;
-    p.partU = h->d_Sraw + lenA;
   }
-  p.nPartU = 1; p.nPartSyrk = 1; p.nPartScal = h->grid_frames; p.rank = h->rank;
+  p.Sraw = h->d_Sraw;
+  p.Uraw = h->d_Sraw + lenS;
+  p.Zy = h->d_Sraw + lenS + lenU;
+  p.nPartScal = h->grid_frames; p.rank = h->rank;
   p.cams = h->d_cams; p.partS = h->d_partS; p.partG = h->d_partG; p.nPartG = L.nTiles;
   p.red = h->d_red;
   p.offS = L.offS; p.offB = L.offB; p.offG = L.offG; p.offDiag = L.offDiag; p.offScal = L.offScal; p.offRank = L.offRank;
@@ -416,7 +437,10 @@ int solve_reduced(mcba_handle* h, double lambda) {
 }
 
 // ------------------------------------------------------------------ K3 back-substitution
-// delta_f = -L^-T (y_f + Z_f^T delta_raw),  x_new = x + delta.  192 threads = 32 frames x 6.
+// delta_f = -L^-T (y_f + Z_f^T delta_raw),  x_new = x + delta.  CTA = 4 warps on one frame tile,
+// lane = frame: warp w sums its quarter of the camera rows of Z^T delta_raw with coalesced
+// 256-byte row loads, warp 0 finishes the 6x6 triangular solve and the step scalars.
+constexpr int kBackWarps = 4;
 struct BackParams {
   int C, nc, rank;
   long long F, nTiles;
@@ -429,13 +453,12 @@ struct BackParams {
   double* part; unsigned int* counter; double* out;  // out[0..3] = |dx|^2, |x|^2, g.dx, dx D2 dx
 };
 
-__global__ void __launch_bounds__(192) backsub_kernel(const BackParams p) {
+__global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackParams p) {
   extern __shared__ double smem[];
-  double* draw = smem;            // [nc]
-  double* sv = draw + p.nc;       // [192]
-  __shared__ double s_red[6 * 4];
+  double* draw = smem;                       // [nc] camera step in the raw basis
+  double* sv = draw + ((p.nc + 1) & ~1);     // [kBackWarps][6][32]
   __shared__ bool s_last;
-  const int tid = threadIdx.x, nc = p.nc;
+  const int tid = threadIdx.x, nc = p.nc, lane = tid & 31, warp = tid >> 5;
   for (int r = tid; r < nc; r += blockDim.x) {
     const int c = r / 12, i = r % 12;
     const double* d = p.dcam + 12 * c;
@@ -448,40 +471,50 @@ __global__ void __launch_bounds__(192) backsub_kernel(const BackParams p) {
   }
   __syncthreads();
   double dd = 0, xx = 0, gd = 0, dDd = 0;
-  const int fl = tid / 6, k = tid % 6;
+  const int r_begin = (nc * warp) / kBackWarps, r_end = (nc * (warp + 1)) / kBackWarps;
   for (long long tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
-    const long long f = tile * kTile + fl;
-    double v = 0.0;
-    if (f < p.F) {
-      const double2* zr = reinterpret_cast<const double2*>(p.Z + ((size_t)f * 6 + k) * nc);
-      double s0 = 0, s1 = 0;
-      for (int r = 0; r < nc / 2; ++r) {
-        const double2 z = zr[r];
-        s0 = fma(z.x, draw[2 * r], s0);
-        s1 = fma(z.y, draw[2 * r + 1], s1);
-      }
-      v = p.y[(size_t)f * 6 + k] + (s0 + s1);
+    const double* z = p.Z + ((size_t)tile * nc) * 6 * kTile + lane;
+    double s[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+    for (int r = r_begin; r < r_end; ++r) {
+      const double dr = draw[r];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] = fma(z[(size_t)(r * 6 + k) * kTile], dr, s[k]);
     }
-    sv[tid] = v;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sv[(warp * 6 + k) * 32 + lane] = s[k];
     __syncthreads();
-    if (f < p.F) {
-      const double* li = p.Linv + (size_t)tile * 21 * kTile + fl;
-      double d = 0.0;
-      for (int j = k; j < 6; ++j) d -= li[(j * (j + 1) / 2 + k) * kTile] * sv[fl * 6 + j];
-      const size_t xi = (size_t)nc + (size_t)f * 6 + k;
-      const double xo = p.x[xi];
-      p.x_new[xi] = xo + d;
-      double d2 = p.D2pose[(size_t)tile * 6 * kTile + k * kTile + fl];
-      if (d2 == 0.0) d2 = 1.0;
-      dd = fma(d, d, dd);
-      xx = fma(xo, xo, xx);
-      gd = fma(p.gpose[(size_t)f * 6 + k], d, gd);
-      dDd = fma(d2 * d, d, dDd);
+    const long long f = tile * kTile + lane;
+    if (warp == 0 && f < p.F) {
+      double v[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double t = p.y[(size_t)tile * 6 * kTile + k * kTile + lane];
+#pragma unroll
+        for (int w = 0; w < kBackWarps; ++w) t += sv[(w * 6 + k) * 32 + lane];
+        v[k] = t;
+      }
+      const double* li = p.Linv + (size_t)tile * 21 * kTile + lane;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        double d = 0.0;
+#pragma unroll
+        for (int j = k; j < 6; ++j) d -= li[(j * (j + 1) / 2 + k) * kTile] * v[j];
+        const size_t xi = (size_t)nc + (size_t)f * 6 + k;
+        const double xo = p.x[xi];
+        p.x_new[xi] = xo + d;
+        double d2 = p.D2pose[(size_t)tile * 6 * kTile + k * kTile + lane];
+        if (d2 == 0.0) d2 = 1.0;
+        dd = fma(d, d, dd);
+        xx = fma(xo, xo, xx);
+        gd = fma(p.gpose[(size_t)f * 6 + k], d, gd);
+        dDd = fma(d2 * d, d, dDd);
+      }
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0) {
-    for (int r = tid; r < nc; r += blockDim.x) {
+  if (blockIdx.x == 0 && warp == 0) {
+    for (int r = lane; r < nc; r += 32) {
       const double d = p.dcam[r], xo = p.x[r];
       p.x_new[r] = xo + d;
       if (p.rank == 0) {  // camera terms are counted once across ranks
@@ -494,29 +527,27 @@ __global__ void __launch_bounds__(192) backsub_kernel(const BackParams p) {
       }
     }
   }
+  // only warp 0 holds step scalars
+  if (warp == 0) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    dd += __shfl_xor_sync(0xffffffffu, dd, off);
-    xx += __shfl_xor_sync(0xffffffffu, xx, off);
-    gd += __shfl_xor_sync(0xffffffffu, gd, off);
-    dDd += __shfl_xor_sync(0xffffffffu, dDd, off);
-  }
-  const int lane = tid & 31, warp = tid >> 5;
-  if (lane == 0) { s_red[warp * 4] = dd; s_red[warp * 4 + 1] = xx; s_red[warp * 4 + 2] = gd; s_red[warp * 4 + 3] = dDd; }
-  __syncthreads();
-  if (tid == 0) {
-    double a = 0, b = 0, c = 0, d = 0;
-    for (int w = 0; w < 6; ++w) { a += s_red[w * 4]; b += s_red[w * 4 + 1]; c += s_red[w * 4 + 2]; d += s_red[w * 4 + 3]; }
-    double* o = p.part + (size_t)blockIdx.x * 4;
-    o[0] = a; o[1] = b; o[2] = c; o[3] = d;
-    __threadfence();
-    s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
+    for (int off = 16; off >= 1; off >>= 1) {
+      dd += __shfl_xor_sync(0xffffffffu, dd, off);
+      xx += __shfl_xor_sync(0xffffffffu, xx, off);
+      gd += __shfl_xor_sync(0xffffffffu, gd, off);
+      dDd += __shfl_xor_sync(0xffffffffu, dDd, off);
+    }
+    if (lane == 0) {
+      double* o = p.part + (size_t)blockIdx.x * 4;
+      o[0] = dd; o[1] = xx; o[2] = gd; o[3] = dDd;
+      __threadfence();
+      s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
+    }
   }
   __syncthreads();
-  if (s_last) {
+  if (s_last && warp == 0) {
     __threadfence();
     double a = 0, b = 0, c = 0, d = 0;
-    for (unsigned i = tid; i < gridDim.x; i += blockDim.x) {
+    for (unsigned i = lane; i < gridDim.x; i += 32) {
       a += __ldcg(p.part + i * 4); b += __ldcg(p.part + i * 4 + 1); c += __ldcg(p.part + i * 4 + 2); d += __ldcg(p.part + i * 4 + 3);
     }
 #pragma unroll
@@ -526,12 +557,7 @@ __global__ void __launch_bounds__(192) backsub_kernel(const BackParams p) {
       c += __shfl_xor_sync(0xffffffffu, c, off);
       d += __shfl_xor_sync(0xffffffffu, d, off);
     }
-    __syncthreads();
-    if (lane == 0) { s_red[warp * 4] = a; s_red[warp * 4 + 1] = b; s_red[warp * 4 + 2] = c; s_red[warp * 4 + 3] = d; }
-    __syncthreads();
-    if (tid == 0) {
-      a = b = c = d = 0;
-      for (int w = 0; w < 6; ++w) { a += s_red[w * 4]; b += s_red[w * 4 + 1]; c += s_red[w * 4 + 2]; d += s_red[w * 4 + 3]; }
+    if (lane == 0) {
       p.out[0] = a; p.out[1] = b; p.out[2] = c; p.out[3] = d;
       *p.counter = 0;
     }
@@ -549,7 +575,7 @@ int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda
   p.part = h->d_scal + 64 + 3 * 4096;                                     // [grid_back][4]
   p.counter = reinterpret_cast<unsigned int*>(h->d_scal + 33);
   p.out = h->d_scal + 8;
-  backsub_kernel<<<h->grid_back, 192, sizeof(double) * (L.nc + 192), h->stream>>>(p);
+  backsub_kernel<<<h->grid_back, kBackWarps * 32, sizeof(double) * (((L.nc + 1) & ~1) + kBackWarps * 6 * 32), h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

@@ -149,6 +149,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   L.nTiles = (F + kTile - 1) / kTile;
   L.Fpad = L.nTiles * kTile;
   L.nc = 12 * C;
+  L.nc8 = (L.nc + 7) / 8 * 8;
   L.offS = 0;
   L.offB = (long long)L.nc * L.nc;
   L.offG = L.offB + L.nc;
@@ -165,7 +166,6 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
   h->grid_back = (int)std::min<long long>(L.nTiles, 8LL * h->n_sm);
   const long long n = L.nc + 6 * F;
-  const int nb = L.nc / 6, nT = nb * (nb + 1) / 2;
   auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8); };
 #define MCBA_ALLOC(ptr, count) MCBA_CUDA(alloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
   MCBA_ALLOC(h->d_obs_ref, (size_t)C * F * N * 2);
@@ -185,8 +185,9 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_ALLOC(h->d_partG, L.nTiles);
   MCBA_ALLOC(h->d_partU, (size_t)h->grid_frames * C * kAcc);
   MCBA_ALLOC(h->d_partS, (size_t)h->grid_frames * kRsNum);
-  MCBA_ALLOC(h->d_partSyrk, (size_t)h->grid_syrk * ((size_t)nT * 36 + (size_t)nb * 6));
-  MCBA_ALLOC(h->d_Sraw, (size_t)nT * 36 + (size_t)nb * 6 + (size_t)C * kAcc);
+  MCBA_ALLOC(h->d_partSyrk, (size_t)h->grid_syrk * L.nc8 * L.nc8);
+  MCBA_ALLOC(h->d_partZy, (size_t)L.nTiles * L.nc);
+  MCBA_ALLOC(h->d_Sraw, (size_t)L.nc8 * L.nc8 + L.nc + (size_t)C * kAcc);
   MCBA_ALLOC(h->d_red, L.redLen);
   MCBA_ALLOC(h->d_Sd, (size_t)L.nc * L.nc);
   MCBA_ALLOC(h->d_dcam, 2 * L.nc);
@@ -197,6 +198,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_CUDA(cudaMemset(h->d_scal, 0, sizeof(double) * (64 + 7 * 4096)));
   MCBA_CUDA(cudaMemset(h->d_info, 0, sizeof(int) * 4));
   MCBA_CUDA(cudaMemset(h->d_gpose, 0, sizeof(double) * L.Fpad * 6));
+  MCBA_CUDA(cudaMemset(h->d_partSyrk, 0, sizeof(double) * (size_t)h->grid_syrk * L.nc8 * L.nc8));   // lower block triangle is never written
   MCBA_CUDA(cudaMallocHost((void**)&h->h_pinned, sizeof(double) * (L.redLen + 64)));
   if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) {
     set_error("cusolverDnCreate failed");
@@ -219,7 +221,7 @@ int mcba_destroy(mcba_handle* h) {
   if (h->solver) cusolverDnDestroy(h->solver);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
-                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_partG};
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_partG, h->d_partZy};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {
     for (int i = 0; i < kProfEvents * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);

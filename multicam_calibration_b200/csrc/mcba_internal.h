@@ -29,7 +29,8 @@ constexpr int kAcc = 128;  // accumulator slots of the raw 12x12 block + q per c
 struct Layout {
   int C = 0, N = 0;
   long long F = 0, nTiles = 0, Fpad = 0;
-  int nc = 0;  // 12 C
+  int nc = 0;   // 12 C
+  int nc8 = 0;  // nc rounded up to a multiple of 8 (DMMA tile rows of the SYRK)
   // packed reduced buffer offsets (doubles)
   long long offS = 0, offB = 0, offG = 0, offDiag = 0, offScal = 0, offRank = 0, redLen = 0;
 };
@@ -57,6 +58,7 @@ struct mcba_handle {
   mcba::CamConst* d_cams = nullptr;
   double* d_H = nullptr;      // K2p -> K2c hand-off [tile][c][63][32]
   double* d_partG = nullptr;  // [nTiles] max |pose gradient| per tile
+  double* d_partZy = nullptr; // [nTiles][12C] per-tile sums of Z_f y_f
   double* d_Z = nullptr;
   double* d_Linv = nullptr;
   double* d_y = nullptr;
@@ -66,7 +68,7 @@ struct mcba_handle {
   double* d_partU = nullptr;
   double* d_partS = nullptr;
   double* d_partSyrk = nullptr;
-  double* d_Sraw = nullptr;   // 12C x 12C raw-basis sum Z Z^T  | b part
+  double* d_Sraw = nullptr;   // [nc8 x nc8 raw-basis sum Z Z^T (upper 8x8 tiles) | Z y (12C) | U partial sums (C x kAcc)]
   double* d_red = nullptr;    // packed reduced system (see Layout)
   double* d_Sd = nullptr;     // damped copy handed to potrf
   double* d_dcam = nullptr;   // [delta_cam true (12C) | delta_cam raw (12C)]
