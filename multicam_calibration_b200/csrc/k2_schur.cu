@@ -50,52 +50,63 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 constexpr int kSyrkStages = 3;
-constexpr int kSyrkWarps = 8;
-constexpr int kZK = 6 * kTile;   // K extent of one tile of Z
+constexpr int kSyrkWarps = 8;     // consumer (DMMA) warps; warp kSyrkWarps is the copy producer
+constexpr int kZK = 6 * kTile;    // K extent of one tile of Z
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 struct SyrkParams {
   const double* Z;
   int nc, nc8, nb8, nT;      // rows, rows padded to 8, row blocks, upper-triangle 8x8 tiles
-  long long nTiles;
+  int nTiles;                // frame tiles
   int KW;                    // K width of one stage (divides 192, multiple of 4)
   double* part;              // [gridDim.x][nc8 * nc8]
 };
 
+// this warp's share of the nT tiles handled by CTA column blockIdx.y: [t0, t0 + cnt)
+__device__ __forceinline__ void syrk_tile_range(const SyrkParams& p, int warp, int& t0, int& cnt) {
+  const int per_col = (p.nT + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int c0 = (int)blockIdx.y * per_col;
+  const int n = min(per_col, p.nT - c0) > 0 ? min(per_col, p.nT - c0) : 0;
+  const int base = n / kSyrkWarps, extra = n % kSyrkWarps;
+  // the last `extra` warps take one more tile (keeps the scheduler that also hosts the producer warp light)
+  const int first_big = kSyrkWarps - extra;
+  cnt = base + (warp >= first_big ? 1 : 0);
+  t0 = c0 + warp * base + (warp > first_big ? warp - first_big : 0);
+}
+
 template <int NT>
-__global__ void __launch_bounds__(kSyrkWarps * 32, 1) k2_syrk_kernel(const SyrkParams p) {
+__device__ __forceinline__ void syrk_stage(const double* __restrict__ st, const int (&offA)[12], const int (&offB)[12],
+                                           double (&acc)[12][2], int KW) {
+#pragma unroll 4
+  for (int k0 = 0; k0 < KW; k0 += 4) {
+#pragma unroll
+    for (int sl = 0; sl < NT; ++sl) {
+      const double a = st[offA[sl] + k0];
+      const double b = st[offB[sl] + k0];
+      dmma_m8n8k4(acc[sl][0], acc[sl][1], a, b);
+    }
+  }
+}
+
+__global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const SyrkParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ unsigned long long full_bar[kSyrkStages];
+  __shared__ unsigned long long full_bar[kSyrkStages], empty_bar[kSyrkStages];
   double* stages = reinterpret_cast<double*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ld = p.KW + 4;
   const size_t stage_doubles = (size_t)p.nc8 * ld;
-
-  // this warp's tiles: NT consecutive tiles of the row-major upper block triangle
-  int offA[NT], offB[NT];
-  bool valid[NT];
-  {
-    const int t0 = ((int)blockIdx.y * kSyrkWarps + warp) * NT;
-    int I = 0, rem = t0;
-    while (I < p.nb8 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
-    int J = I + rem;
-#pragma unroll
-    for (int s = 0; s < NT; ++s) {
-      valid[s] = t0 + s < p.nT;
-      offA[s] = (I * 8 + (lane >> 2)) * ld + (lane & 3);
-      offB[s] = (J * 8 + (lane >> 2)) * ld + (lane & 3);
-      if (valid[s]) { ++J; if (J == p.nb8) { ++I; J = I; } }
-    }
-  }
-  double acc[NT][2];
-#pragma unroll
-  for (int s = 0; s < NT; ++s) acc[s][0] = acc[s][1] = 0.0;
-
   const int chunks = kZK / p.KW;
-  const long long my_tiles = p.nTiles > blockIdx.x ? (p.nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long long n_units = my_tiles * chunks;
+  const int my_tiles = p.nTiles > (int)blockIdx.x ? (p.nTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_units = my_tiles * chunks;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kSyrkStages; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < kSyrkStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kSyrkWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // padding rows nc .. nc8-1 are never written by the copies: zero them once
@@ -103,49 +114,75 @@ __global__ void __launch_bounds__(kSyrkWarps * 32, 1) k2_syrk_kernel(const SyrkP
     for (int i = threadIdx.x; i < (p.nc8 - p.nc) * ld; i += blockDim.x) stages[s * stage_doubles + (size_t)p.nc * ld + i] = 0.0;
   __syncthreads();
 
-  auto issue = [&](long long unit) {   // called by all lanes of warp 0
-    const int s = (int)(unit % kSyrkStages);
-    const long long tile = blockIdx.x + (unit / chunks) * gridDim.x;
-    const int ch = (int)(unit % chunks);
-    double* dst = stages + (size_t)s * stage_doubles;
-    const double* src = p.Z + ((size_t)tile * p.nc) * kZK + (size_t)ch * p.KW;
-    if (lane == 0) mbar_expect_tx(&full_bar[s], (unsigned)(p.nc * p.KW * sizeof(double)));
-    __syncwarp();
-    for (int r = lane; r < p.nc; r += 32)
-      tma_load_1d(dst + (size_t)r * ld, src + (size_t)r * kZK, (unsigned)(p.KW * sizeof(double)), &full_bar[s]);
-  };
-  if (warp == 0) {
-    for (long long u = 0; u < kSyrkStages && u < n_units; ++u) issue(u);
-  }
-  for (long long unit = 0; unit < n_units; ++unit) {
-    const int s = (int)(unit % kSyrkStages);
-    mbar_wait(&full_bar[s], (unsigned)((unit / kSyrkStages) & 1));
-    const double* st = stages + (size_t)s * stage_doubles;
-#pragma unroll 2
-    for (int k0 = 0; k0 < p.KW; k0 += 4) {
-#pragma unroll
-      for (int sl = 0; sl < NT; ++sl) {
-        if (valid[sl]) {
-          const double a = st[offA[sl] + k0];
-          const double b = st[offB[sl] + k0];
-          dmma_m8n8k4(acc[sl][0], acc[sl][1], a, b);
-        }
-      }
+  if (warp == kSyrkWarps) {
+    // ---------------- producer: one bulk copy per row of the (tile, K-chunk) stage ----------------
+    int tile = blockIdx.x, ch = 0;
+    for (int unit = 0; unit < n_units; ++unit) {
+      const int s = unit % kSyrkStages;
+      if (unit >= kSyrkStages) mbar_wait(&empty_bar[s], (unsigned)((unit / kSyrkStages - 1) & 1));
+      double* dst = stages + (size_t)s * stage_doubles;
+      const double* src = p.Z + ((size_t)tile * p.nc) * kZK + (size_t)ch * p.KW;
+      if (lane == 0) mbar_expect_tx(&full_bar[s], (unsigned)(p.nc * p.KW * sizeof(double)));
+      __syncwarp();
+      for (int r = lane; r < p.nc; r += 32)
+        tma_load_1d(dst + (size_t)r * ld, src + (size_t)r * kZK, (unsigned)(p.KW * sizeof(double)), &full_bar[s]);
+      if (++ch == chunks) { ch = 0; tile += gridDim.x; }
     }
-    __syncthreads();   // everyone is done with stage s: refill it
-    if (warp == 0 && unit + kSyrkStages < n_units) issue(unit + kSyrkStages);
+    return;
   }
 
-  // one partial per CTA column; tiles of different blockIdx.y are disjoint
+  // ---------------- consumers: up to 12 tiles of the upper block triangle per warp ----------------
+  int t0, cnt;
+  syrk_tile_range(p, warp, t0, cnt);
+  int offA[12], offB[12];
+  {
+    int I = 0, rem = t0;
+    while (I < p.nb8 - 1 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
+    int J = I + rem;
+    if (J >= p.nb8) { I = 0; J = 0; }   // empty range
+#pragma unroll
+    for (int s = 0; s < 12; ++s) {
+      offA[s] = (I * 8 + (lane >> 2)) * ld + (lane & 3);
+      offB[s] = (J * 8 + (lane >> 2)) * ld + (lane & 3);
+      if (s + 1 < cnt) { ++J; if (J == p.nb8) { ++I; J = I; } }
+    }
+  }
+  double acc[12][2];
+#pragma unroll
+  for (int s = 0; s < 12; ++s) acc[s][0] = acc[s][1] = 0.0;
+
+  for (int unit = 0; unit < n_units; ++unit) {
+    const int s = unit % kSyrkStages;
+    mbar_wait(&full_bar[s], (unsigned)((unit / kSyrkStages) & 1));
+    const double* st = stages + (size_t)s * stage_doubles;
+    switch (cnt) {   // warp-uniform: exact trip counts, no predicated DMMA
+      case 1: syrk_stage<1>(st, offA, offB, acc, p.KW); break;
+      case 2: syrk_stage<2>(st, offA, offB, acc, p.KW); break;
+      case 3: syrk_stage<3>(st, offA, offB, acc, p.KW); break;
+      case 4: syrk_stage<4>(st, offA, offB, acc, p.KW); break;
+      case 5: syrk_stage<5>(st, offA, offB, acc, p.KW); break;
+      case 6: syrk_stage<6>(st, offA, offB, acc, p.KW); break;
+      case 7: syrk_stage<7>(st, offA, offB, acc, p.KW); break;
+      case 8: syrk_stage<8>(st, offA, offB, acc, p.KW); break;
+      case 9: syrk_stage<9>(st, offA, offB, acc, p.KW); break;
+      case 10: syrk_stage<10>(st, offA, offB, acc, p.KW); break;
+      case 11: syrk_stage<11>(st, offA, offB, acc, p.KW); break;
+      case 12: syrk_stage<12>(st, offA, offB, acc, p.KW); break;
+      default: break;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // one partial per CTA column; tiles of different warps / blockIdx.y are disjoint
   double* out = p.part + (size_t)blockIdx.x * p.nc8 * p.nc8;
   {
-    const int t0 = ((int)blockIdx.y * kSyrkWarps + warp) * NT;
     int I = 0, rem = t0;
-    while (I < p.nb8 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
+    while (I < p.nb8 - 1 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
     int J = I + rem;
 #pragma unroll
-    for (int s = 0; s < NT; ++s) {
-      if (valid[s]) {
+    for (int s = 0; s < 12; ++s) {
+      if (s < cnt) {
         *reinterpret_cast<double2*>(out + (size_t)(I * 8 + (lane >> 2)) * p.nc8 + J * 8 + 2 * (lane & 3)) =
             make_double2(acc[s][0], acc[s][1]);
         ++J;
@@ -156,16 +193,14 @@ __global__ void __launch_bounds__(kSyrkWarps * 32, 1) k2_syrk_kernel(const SyrkP
 }
 
 struct SyrkConfig {
-  int NT, gy, KW;
+  int gy, KW;
   size_t smem;
 };
 
 static SyrkConfig syrk_config(int nc) {
   SyrkConfig c;
   const int nc8 = (nc + 7) / 8 * 8, nb8 = nc8 / 8, nT = nb8 * (nb8 + 1) / 2;
-  const int per_warp = (nT + kSyrkWarps - 1) / kSyrkWarps;
-  c.NT = per_warp <= 3 ? 3 : (per_warp <= 6 ? 6 : 12);
-  c.gy = (nT + kSyrkWarps * c.NT - 1) / (kSyrkWarps * c.NT);
+  c.gy = (nT + kSyrkWarps * 12 - 1) / (kSyrkWarps * 12);   // at most 12 tiles (24 accumulator doubles) per warp
   static const int widths[] = {192, 96, 64, 48, 32, 16, 8};
   c.KW = 8;
   for (int w : widths) {
@@ -187,19 +222,11 @@ int launch_k2_syrk(mcba_handle* h) {
   SyrkParams p;
   p.Z = h->d_Z;
   p.nc = L.nc; p.nc8 = L.nc8; p.nb8 = L.nc8 / 8; p.nT = p.nb8 * (p.nb8 + 1) / 2;
-  p.nTiles = L.nTiles;
+  p.nTiles = (int)L.nTiles;
   p.KW = c.KW;
   p.part = h->d_partSyrk;
-  const dim3 grid(h->grid_syrk, c.gy);
-#define MCBA_SYRK_LAUNCH(NTV)                                                                                         \
-  do {                                                                                                                \
-    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));    \
-    k2_syrk_kernel<NTV><<<grid, kSyrkWarps * 32, c.smem, h->stream>>>(p);                                              \
-  } while (0)
-  if (c.NT == 3) MCBA_SYRK_LAUNCH(3);
-  else if (c.NT == 6) MCBA_SYRK_LAUNCH(6);
-  else MCBA_SYRK_LAUNCH(12);
-#undef MCBA_SYRK_LAUNCH
+  MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+  k2_syrk_kernel<<<dim3(h->grid_syrk, c.gy), (kSyrkWarps + 1) * 32, c.smem, h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
