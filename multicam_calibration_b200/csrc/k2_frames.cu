@@ -48,10 +48,110 @@ __device__ __forceinline__ void pose_map(const CamConst& cam, const double (&pos
   cross_mat3(tcf, Rc, K);
 }
 
+// Camera c's contribution to the pose block of this lane's frame: V'' += E'^T A_ee E', g'' += E'^T q_e.
+// h: this lane's hand-off column of the pair (global or shared memory), entries kTile doubles apart.
+__device__ __forceinline__ void pose_block_add(const double* __restrict__ h, const double (&Rc)[9], const double (&K)[9],
+                                               double (&Vpp)[21], double (&gpp)[6]) {
+  double Aee[21], qe[6];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) Aee[i] = h[(36 + i) * kTile];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) qe[i] = h[(57 + i) * kTile];
+  double Be[36];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      Be[r * 6 + k] = Aee[sym6(r, 0)] * Rc[k] + Aee[sym6(r, 1)] * Rc[3 + k] + Aee[sym6(r, 2)] * Rc[6 + k] +
+                      Aee[sym6(r, 3)] * K[k] + Aee[sym6(r, 4)] * K[3 + k] + Aee[sym6(r, 5)] * K[6 + k];
+      Be[r * 6 + 3 + k] = Aee[sym6(r, 3)] * Rc[k] + Aee[sym6(r, 4)] * Rc[3 + k] + Aee[sym6(r, 5)] * Rc[6 + k];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+#pragma unroll
+    for (int n = a; n < 6; ++n) {
+      double v;
+      if (a < 3) {
+        v = Rc[a] * Be[n] + Rc[3 + a] * Be[6 + n] + Rc[6 + a] * Be[12 + n] + K[a] * Be[18 + n] +
+            K[3 + a] * Be[24 + n] + K[6 + a] * Be[30 + n];
+      } else {
+        v = Rc[a - 3] * Be[18 + n] + Rc[3 + a - 3] * Be[24 + n] + Rc[6 + a - 3] * Be[30 + n];
+      }
+      Vpp[tri6(a, n)] += v;
+    }
+    if (a < 3) {
+      gpp[a] += Rc[a] * qe[0] + Rc[3 + a] * qe[1] + Rc[6 + a] * qe[2] + K[a] * qe[3] + K[3 + a] * qe[4] +
+                K[6 + a] * qe[5];
+    } else {
+      gpp[a] += Rc[a - 3] * qe[3] + Rc[3 + a - 3] * qe[4] + Rc[6 + a - 3] * qe[5];
+    }
+  }
+}
+
+// Z_cf = (A[:,ext] E' P') L^-T for one camera, one raw camera row at a time, written as coalesced
+// rows of the tile's Z block (z points at [row 12c][k 0][lane]); zy[row] += sum_k Z[row][k] y[k].
+__device__ __forceinline__ void z_rows(const double* __restrict__ h, const double (&Rc)[9], const double (&K)[9],
+                                       const double (&Jl)[9], const double (&Linv)[21], const double (&yv)[6],
+                                       double* __restrict__ z, double (&zy)[12]) {
+#pragma unroll
+  for (int row = 0; row < 12; ++row) {
+    double am[3], ag[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      am[j] = row < 6 ? h[(row * 6 + j) * kTile] : h[(36 + sym6(row - 6, j)) * kTile];
+      ag[j] = row < 6 ? h[(row * 6 + 3 + j) * kTile] : h[(36 + sym6(row - 6, 3 + j)) * kTile];
+    }
+    double b[6], zr[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      b[k] = am[0] * Rc[k] + am[1] * Rc[3 + k] + am[2] * Rc[6 + k] + ag[0] * K[k] + ag[1] * K[3 + k] + ag[2] * K[6 + k];
+      b[3 + k] = ag[0] * Rc[k] + ag[1] * Rc[3 + k] + ag[2] * Rc[6 + k];
+    }
+    z_row(b, Jl, Linv, zr);
+    double t = zy[row];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      z[(size_t)(row * 6 + k) * kTile] = zr[k];   // padded lanes carry zeros (their hand-off is zero)
+      t = fma(zr[k], yv[k], t);
+    }
+    zy[row] = t;
+  }
+}
+
+// lane l < 12 receives the sum over the warp of zy[l]
+__device__ __forceinline__ double zy_lane_sum(double (&zy)[12], int lane) {
+#pragma unroll
+  for (int row = 0; row < 12; ++row) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) zy[row] += __shfl_xor_sync(0xffffffffu, zy[row], off);
+  }
+  double v = zy[0];
+#pragma unroll
+  for (int row = 1; row < 12; ++row) v = lane == row ? zy[row] : v;
+  return v;
+}
+
+__device__ __forceinline__ void store_pose_outputs(const K2CParams& p, long long tile, long long f, bool fvalid, int lane,
+                                                   const double (&Linv)[21], const double (&yv)[6], const double (&gp)[6]) {
+  double* lo = p.Linv + (size_t)tile * 21 * 32 + lane;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) lo[i * 32] = Linv[i];
+  double* yo = p.y + (size_t)tile * 6 * 32 + lane;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) yo[i * 32] = yv[i];
+  if (fvalid) {
+#pragma unroll
+    for (int i = 0; i < 6; i += 2)
+      *reinterpret_cast<double2*>(p.gpose + (size_t)f * 6 + i) = make_double2(gp[i], gp[i + 1]);
+  }
+}
+
+// General path (any camera count): one CTA per frame tile, warp w handles cameras w, w + kW, ...
+// reading the hand-off from global memory; partial outputs per tile.
 template <int kW>
 __global__ void __launch_bounds__(kW * 32, 2) k2c_kernel(const K2CParams p) {
   __shared__ double s_V[kW][27][32];
-  __shared__ double s_g[kW];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = p.C, nc = 12 * C;
   const long long tile = blockIdx.x;
@@ -63,7 +163,6 @@ __global__ void __launch_bounds__(kW * 32, 2) k2c_kernel(const K2CParams p) {
   double Jl[9];
   so3_left_jacobian(pose, Jl);
 
-  // ---- V'' = sum_c E'^T A_ee E', g'' = sum_c E'^T q_e over this warp's cameras
   double Vpp[21], gpp[6];
 #pragma unroll
   for (int i = 0; i < 21; ++i) Vpp[i] = 0.0;
@@ -72,44 +171,9 @@ __global__ void __launch_bounds__(kW * 32, 2) k2c_kernel(const K2CParams p) {
   for (int c = warp; c < C; c += kW) {
     double Rc[9], K[9];
     pose_map(p.cams[c], pose, Rc, K);
-    const double* h = p.H + ((size_t)(tile * C + c) * kHandoff) * kTile + lane;
-    double Aee[21], qe[6];
-#pragma unroll
-    for (int i = 0; i < 21; ++i) Aee[i] = h[(size_t)(36 + i) * kTile];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) qe[i] = h[(size_t)(57 + i) * kTile];
-    double Be[36];
-#pragma unroll
-    for (int r = 0; r < 6; ++r) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        Be[r * 6 + k] = Aee[sym6(r, 0)] * Rc[k] + Aee[sym6(r, 1)] * Rc[3 + k] + Aee[sym6(r, 2)] * Rc[6 + k] +
-                        Aee[sym6(r, 3)] * K[k] + Aee[sym6(r, 4)] * K[3 + k] + Aee[sym6(r, 5)] * K[6 + k];
-        Be[r * 6 + 3 + k] = Aee[sym6(r, 3)] * Rc[k] + Aee[sym6(r, 4)] * Rc[3 + k] + Aee[sym6(r, 5)] * Rc[6 + k];
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-      for (int n = a; n < 6; ++n) {
-        double v;
-        if (a < 3) {
-          v = Rc[a] * Be[n] + Rc[3 + a] * Be[6 + n] + Rc[6 + a] * Be[12 + n] + K[a] * Be[18 + n] +
-              K[3 + a] * Be[24 + n] + K[6 + a] * Be[30 + n];
-        } else {
-          v = Rc[a - 3] * Be[18 + n] + Rc[3 + a - 3] * Be[24 + n] + Rc[6 + a - 3] * Be[30 + n];
-        }
-        Vpp[tri6(a, n)] += v;
-      }
-      if (a < 3) {
-        gpp[a] += Rc[a] * qe[0] + Rc[3 + a] * qe[1] + Rc[6 + a] * qe[2] + K[a] * qe[3] + K[3 + a] * qe[4] +
-                  K[6 + a] * qe[5];
-      } else {
-        gpp[a] += Rc[a - 3] * qe[3] + Rc[3 + a - 3] * qe[4] + Rc[6 + a - 3] * qe[5];
-      }
-    }
+    pose_block_add(p.H + ((size_t)(tile * C + c) * kHandoff) * kTile + lane, Rc, K, Vpp, gpp);
   }
-  // ---- exchange the partial sums (every warp then holds the full pose block; fixed order)
+  // exchange the partial sums (every warp then holds the full pose block; fixed order)
   if (kW > 1) {
 #pragma unroll
     for (int i = 0; i < 21; ++i) s_V[warp][i][lane] = Vpp[i];
@@ -131,67 +195,136 @@ __global__ void __launch_bounds__(kW * 32, 2) k2c_kernel(const K2CParams p) {
   double Linv[21], yv[6], gp[6], gmax = 0.0;
   pose_block_factor(Vpp, gpp, Jl, p.lambda, p.D2pose + (size_t)tile * 6 * 32 + lane, warp == 0, Linv, yv, gp, gmax);
   if (warp == 0) {
-    double* lo = p.Linv + (size_t)tile * 21 * 32 + lane;
-#pragma unroll
-    for (int i = 0; i < 21; ++i) lo[i * 32] = Linv[i];
-    double* yo = p.y + (size_t)tile * 6 * 32 + lane;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) yo[i * 32] = yv[i];
-    if (fvalid) {
-#pragma unroll
-      for (int i = 0; i < 6; i += 2)
-        *reinterpret_cast<double2*>(p.gpose + (size_t)f * 6 + i) = make_double2(gp[i], gp[i + 1]);
-    }
+    store_pose_outputs(p, tile, f, fvalid, lane, Linv, yv, gp);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
     if (lane == 0) p.partG[tile] = gmax;
   }
-  // ---- Z_cf = (A[:,ext] E' P') L^-T for this warp's cameras, one raw camera row at a time
   for (int c = warp; c < C; c += kW) {
     double Rc[9], K[9];
     pose_map(p.cams[c], pose, Rc, K);
-    const double* h = p.H + ((size_t)(tile * C + c) * kHandoff) * kTile + lane;
-    double* z = p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane;
     double zy[12];
 #pragma unroll
-    for (int row = 0; row < 12; ++row) {
-      double am[3], ag[3];
+    for (int i = 0; i < 12; ++i) zy[i] = 0.0;
+    z_rows(p.H + ((size_t)(tile * C + c) * kHandoff) * kTile + lane, Rc, K, Jl, Linv, yv,
+           p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane, zy);
+    const double v = zy_lane_sum(zy, lane);
+    if (lane < 12) p.partZy[(size_t)tile * nc + c * 12 + lane] = v;
+  }
+}
+
+// Ring path (kC <= 6 cameras, warp = camera): persistent CTAs, the whole hand-off block of a tile
+// (kC x 63 x 32 doubles, contiguous) arrives by ONE bulk async copy into a 2-stage shared-memory
+// ring while the previous tile is being processed, so no warp ever waits on a global load; Z, y and
+// L^-1 leave as coalesced 256-byte rows.  Partial outputs (Z y, max |g|) per CTA.
+__device__ __forceinline__ unsigned k2c_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k2c_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "K2C_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra K2C_WAIT_DONE;\n"
+      "bra K2C_WAIT_LOOP;\n"
+      "K2C_WAIT_DONE:\n"
+      "}\n" ::"r"(k2c_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int kC>
+__global__ void __launch_bounds__(kC * 32, 1) k2c_ring_kernel(const K2CParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ unsigned long long full_bar[2];
+  constexpr int kStage = kC * kHandoff * kTile;                  // doubles per stage
+  double* stages = reinterpret_cast<double*>(smem_raw);          // [2][kC][63][32]
+  double* s_V = stages + 2 * kStage;                             // [kC][21][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nc = 12 * kC;
+  const int c = warp;
+  const int n_it = p.nTiles > blockIdx.x ? (int)((p.nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  auto issue = [&](int it) {   // thread 0 only
+    const long long tile = blockIdx.x + (long long)it * gridDim.x;
+    const unsigned bytes = kStage * sizeof(double);
+    unsigned long long* bar = &full_bar[it & 1];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2c_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     k2c_smem_u32(stages + (size_t)(it & 1) * kStage)),
+                 "l"(p.H + (size_t)tile * kStage), "r"(bytes), "r"(k2c_smem_u32(bar))
+                 : "memory");
+  };
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(&full_bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(&full_bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (n_it > 0) issue(0);
+    if (n_it > 1) issue(1);
+  }
+  __syncthreads();
+  const CamConst& cam = p.cams[c];
+  double zy[12], gmax = 0.0;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        am[j] = row < 6 ? h[(size_t)(row * 6 + j) * kTile] : h[(size_t)(36 + sym6(row - 6, j)) * kTile];
-        ag[j] = row < 6 ? h[(size_t)(row * 6 + 3 + j) * kTile] : h[(size_t)(36 + sym6(row - 6, 3 + j)) * kTile];
-      }
-      double b[6], zr[6];
+  for (int i = 0; i < 12; ++i) zy[i] = 0.0;
+
+  for (int it = 0; it < n_it; ++it) {
+    const long long tile = blockIdx.x + (long long)it * gridDim.x;
+    const long long f = tile * kTile + lane;
+    const bool fvalid = f < p.F;
+    double pose[6];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        b[k] = am[0] * Rc[k] + am[1] * Rc[3 + k] + am[2] * Rc[6 + k] + ag[0] * K[k] + ag[1] * K[3 + k] +
-               ag[2] * K[6 + k];
-        b[3 + k] = ag[0] * Rc[k] + ag[1] * Rc[3 + k] + ag[2] * Rc[6 + k];
-      }
-      z_row(b, Jl, Linv, zr);
-      double t = 0.0;
+    for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
+    double Jl[9], Rc[9], K[9];
+    so3_left_jacobian(pose, Jl);
+    pose_map(cam, pose, Rc, K);
+    k2c_mbar_wait(&full_bar[it & 1], (unsigned)((it >> 1) & 1));
+    double* h = stages + (size_t)(it & 1) * kStage + (size_t)c * kHandoff * kTile + lane;
+    double Vpp[21], gpp[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        z[(size_t)(row * 6 + k) * kTile] = zr[k];   // padded lanes carry zeros (their hand-off is zero)
-        t = fma(zr[k], yv[k], t);
-      }
-      zy[row] = t;
+    for (int i = 0; i < 21; ++i) Vpp[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gpp[i] = 0.0;
+    pose_block_add(h, Rc, K, Vpp, gpp);
+    // exchange: V'' through s_V, g'' through this camera's (already consumed) q_ext slots of the stage
+#pragma unroll
+    for (int i = 0; i < 21; ++i) s_V[(c * 21 + i) * kTile + lane] = Vpp[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) h[(57 + i) * kTile] = gpp[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Vpp[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gpp[i] = 0.0;
+    const double* hq = stages + (size_t)(it & 1) * kStage + lane;
+#pragma unroll
+    for (int w = 0; w < kC; ++w) {
+#pragma unroll
+      for (int i = 0; i < 21; ++i) Vpp[i] += s_V[(w * 21 + i) * kTile + lane];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) gpp[i] += hq[((size_t)w * kHandoff + 57 + i) * kTile];
     }
+    double Linv[21], yv[6], gp[6];
+    pose_block_factor(Vpp, gpp, Jl, p.lambda, p.D2pose + (size_t)tile * 6 * 32 + lane, warp == 0, Linv, yv, gp, gmax);
+    if (warp == 0) store_pose_outputs(p, tile, f, fvalid, lane, Linv, yv, gp);
+    z_rows(h, Rc, K, Jl, Linv, yv, p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane, zy);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic writes (g'') precede the next bulk copy
+    __syncthreads();   // every warp is done with this stage and with s_V
+    if (threadIdx.x == 0 && it + 2 < n_it) issue(it + 2);
+  }
+  const double v = zy_lane_sum(zy, lane);
+  if (lane < 12) p.partZy[(size_t)blockIdx.x * nc + c * 12 + lane] = v;
+  if (warp == 0) {
 #pragma unroll
-    for (int row = 0; row < 12; ++row) {
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) zy[row] += __shfl_xor_sync(0xffffffffu, zy[row], off);
-    }
-    if (lane < 12) {
-      double v = zy[0];
-#pragma unroll
-      for (int row = 1; row < 12; ++row) v = lane == row ? zy[row] : v;
-      p.partZy[(size_t)tile * nc + c * 12 + lane] = v;
-    }
+    for (int off = 16; off >= 1; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+    if (lane == 0) p.partG[blockIdx.x] = gmax;
   }
 }
 
 // ------------------------------------------------------------------ launchers
+// K2c variant and the number of per-CTA partial outputs (Z y, max |g|) it produces.
+int k2_consumer_parts(const Layout& L, int n_sm, bool* ring) {
+  static const bool no_ring = getenv("MCBA_K2C_GENERAL") != nullptr;   // debugging: force the general path
+  *ring = !no_ring && L.C >= 2 && L.C <= 6;
+  return *ring ? (int)(L.nTiles < n_sm ? L.nTiles : n_sm) : (int)L.nTiles;
+}
+
 int k2_producer_grid(const Layout& L, int n_sm, int* warps) {
   // 8 warps per CTA (2 per scheduler at 255 registers) once that still fills the GPU,
   // otherwise narrower CTAs so that small problems spread over more SMs.
@@ -261,10 +394,29 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
   p.D2pose = h->d_D2pose;
   p.partG = h->d_partG;
   p.partZy = h->d_partZy;
-  const int grid = (int)L.nTiles;
-  if (L.C >= 6) k2c_kernel<6><<<grid, 192, 0, h->stream>>>(p);
-  else if (L.C >= 3) k2c_kernel<3><<<grid, 96, 0, h->stream>>>(p);
-  else k2c_kernel<1><<<grid, 32, 0, h->stream>>>(p);
+  if (h->k2c_ring) {
+    const int C = L.C;
+    const size_t smem = sizeof(double) * ((size_t)2 * C * kHandoff * kTile + (size_t)C * 21 * kTile);
+    const int grid = h->n_part_c;
+#define MCBA_K2C_RING(CV)                                                                                          \
+  do {                                                                                                             \
+    MCBA_CUDA(cudaFuncSetAttribute(k2c_ring_kernel<CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    k2c_ring_kernel<CV><<<grid, CV * 32, smem, h->stream>>>(p);                                                     \
+  } while (0)
+    switch (C) {
+      case 2: MCBA_K2C_RING(2); break;
+      case 3: MCBA_K2C_RING(3); break;
+      case 4: MCBA_K2C_RING(4); break;
+      case 5: MCBA_K2C_RING(5); break;
+      default: MCBA_K2C_RING(6); break;
+    }
+#undef MCBA_K2C_RING
+  } else {
+    const int grid = (int)L.nTiles;
+    if (L.C >= 6) k2c_kernel<6><<<grid, 192, 0, h->stream>>>(p);
+    else if (L.C >= 3) k2c_kernel<3><<<grid, 96, 0, h->stream>>>(p);
+    else k2c_kernel<1><<<grid, 32, 0, h->stream>>>(p);
+  }
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

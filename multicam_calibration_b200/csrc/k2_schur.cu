@@ -411,7 +411,7 @@ int launch_finalize(mcba_handle* h) {
     const ReduceSeg s0{h->d_partSyrk, h->grid_syrk, lenS};
     const ReduceSeg s1{h->d_partU, h->grid_frames, lenU};
     reduce_partials_kernel<64, 4><<<(lenS + lenU + 63) / 64, 256, 0, h->stream>>>(s0, s1, h->d_Sraw);
-    const ReduceSeg z0{h->d_partZy, (int)L.nTiles, lenZy};
+    const ReduceSeg z0{h->d_partZy, h->n_part_c, lenZy};
     const ReduceSeg z1{nullptr, 0, 0};
     reduce_partials_kernel<8, 32><<<(lenZy + 7) / 8, 256, 0, h->stream>>>(z0, z1, h->d_Sraw + lenS + lenU);
     h->launches += 2;
@@ -421,7 +421,7 @@ int launch_finalize(mcba_handle* h) {
   p.Uraw = h->d_Sraw + lenS;
   p.Zy = h->d_Sraw + lenS + lenU;
   p.nPartScal = h->grid_frames; p.rank = h->rank;
-  p.cams = h->d_cams; p.partS = h->d_partS; p.partG = h->d_partG; p.nPartG = L.nTiles;
+  p.cams = h->d_cams; p.partS = h->d_partS; p.partG = h->d_partG; p.nPartG = h->n_part_c;
   p.red = h->d_red;
   p.offS = L.offS; p.offB = L.offB; p.offG = L.offG; p.offDiag = L.offDiag; p.offScal = L.offScal; p.offRank = L.offRank;
   finalize_kernel<<<L.C * L.C + 1, 160, 0, h->stream>>>(p);

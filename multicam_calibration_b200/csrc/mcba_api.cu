@@ -162,6 +162,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   h->n_sm = prop.multiProcessorCount;
   MCBA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->grid_frames = k2_producer_grid(L, h->n_sm, &h->prod_warps);
+  h->n_part_c = k2_consumer_parts(L, h->n_sm, &h->k2c_ring);
   h->grid_syrk = syrk_grid(L.nc, F, h->n_sm);
   h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
   h->grid_back = (int)std::min<long long>(L.nTiles, 8LL * h->n_sm);

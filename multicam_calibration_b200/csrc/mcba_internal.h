@@ -57,8 +57,8 @@ struct mcba_handle {
   double* d_xtrial = nullptr;
   mcba::CamConst* d_cams = nullptr;
   double* d_H = nullptr;      // K2p -> K2c hand-off [tile][c][63][32]
-  double* d_partG = nullptr;  // [nTiles] max |pose gradient| per tile
-  double* d_partZy = nullptr; // [nTiles][12C] per-tile sums of Z_f y_f
+  double* d_partG = nullptr;  // [n_part_c] max |pose gradient| per K2c partial
+  double* d_partZy = nullptr; // [n_part_c][12C] partial sums of Z_f y_f
   double* d_Z = nullptr;
   double* d_Linv = nullptr;
   double* d_y = nullptr;
@@ -74,6 +74,8 @@ struct mcba_handle {
   double* d_dcam = nullptr;   // [delta_cam true (12C) | delta_cam raw (12C)]
   double* d_scal = nullptr;   // step scalars (device), partials
   double* h_pinned = nullptr; // pinned host mirror for small read-backs
+  int n_part_c = 0;           // K2c partial outputs (one per tile, or one per persistent CTA on the ring path)
+  bool k2c_ring = false;
   int grid_frames = 0, prod_warps = 8, grid_syrk = 0, grid_cost = 0, grid_back = 0;
   // solver
   cusolverDnHandle_t solver = nullptr;
@@ -112,6 +114,7 @@ int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, doubl
 int launch_k2_producer(mcba_handle* h, const double* x, int loss, double f_scale);
 int launch_k2_consumer(mcba_handle* h, const double* x, double lambda);
 int k2_producer_grid(const mcba::Layout& L, int n_sm, int* warps);
+int k2_consumer_parts(const mcba::Layout& L, int n_sm, bool* ring);
 int launch_k2_syrk(mcba_handle* h);
 int syrk_grid(int nc, long long F, int n_sm);
 int launch_finalize(mcba_handle* h);
