@@ -1,7 +1,10 @@
 // K1 family: camera constants, observation tiling, the materialised residual
 // vector (bundle_adjustment.py:66-98), dense predictions (:33-63), the robust
 // cost, and the per-observation analytic Jacobian blocks used by the parity tests.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+
+#include <cstdlib>
 
 #include "mcba_internal.h"
 #include "mcba_obs.cuh"
@@ -31,22 +34,118 @@ int launch_prep_cameras(mcba_handle* h, const double* x) {
 }
 
 // ---------------------------------------------------------------- observation layouts
-// reference (C,F,N,2)  ->  tiled [tile][c][n][lane] (double2), NaN padded to 32 frames
-__global__ void tile_observations_kernel(const double2* __restrict__ ref, double2* __restrict__ tiled,
-                                         int C, long long F, int N, long long nTiles) {
-  const long long total = nTiles * C * N * kTile;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int lane = (int)(i % kTile);
-    long long r = i / kTile;
-    const int n = (int)(r % N);
-    r /= N;
-    const int c = (int)(r % C);
-    const long long tile = r / C;
-    const long long f = tile * kTile + lane;
-    double2 v = make_double2(nan(""), nan(""));
-    if (f < F) v = ref[((long long)c * F + f) * N + n];
-    tiled[i] = v;
+// reference (C,F,N,2)  ->  tiled [tile][c][n][lane] (double2), NaN padded to 32 frames.
+//
+// Frame order.  Tile slot (tile, lane) holds frame perm[tile*32 + lane] (-1 = padding).  When the
+// camera count is small the frames are sorted (stably) by their visibility mask - bit c set when
+// camera c has at least one finite scalar in the frame - so that the 32 frames of a tile almost
+// always share one mask: a (tile, camera) unit then is either fully observed or empty, empty
+// units are skipped as a whole and no lane idles through a missing view (20 % of the lanes at
+// BASELINE configs[2]).  The order is internal: x, the pose gradient and every C-ABI array stay
+// in the caller's frame order; only the pose loads / stores go through perm.
+
+// visibility mask per frame: one warp per (frame), loops cameras
+__global__ void frame_mask_kernel(const double* __restrict__ ref, int C, long long F, int N,
+                                  unsigned int* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long f = warp; f < F; f += nwarps) {
+    unsigned int m = 0;
+    for (int c = 0; c < C; ++c) {
+      const double* p = ref + ((long long)c * F + f) * 2 * N;
+      bool any = false;
+      for (int s = lane; s < 2 * N; s += 32) any |= p[s] == p[s];
+      if (__any_sync(0xffffffffu, any)) m |= 1u << c;
+    }
+    if (lane == 0) mask[f] = ~m;   // complement: fully observed frames sort first
+  }
+}
+
+__global__ void iota_kernel(int* __restrict__ v, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    v[i] = (int)i;
+}
+
+// perm padding + per-tile active-camera mask
+__global__ void tile_active_kernel(const unsigned int* __restrict__ mask, int* __restrict__ perm, long long F,
+                                   long long nTiles, unsigned int* __restrict__ active) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long tile = warp; tile < nTiles; tile += nwarps) {
+    const long long slot = tile * kTile + lane;
+    unsigned int m = 0;
+    if (slot < F) m = ~mask[perm[slot]];
+    else perm[slot] = -1;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
+    if (lane == 0) active[tile] = m;
+  }
+}
+
+// Live (tile, camera) units, compacted per camera in tile order: units[c][k] = k-th tile in which
+// camera c has observations, count[c] of them.  One CTA per camera.  K2p walks only these.
+__global__ void __launch_bounds__(256) build_units_kernel(const unsigned int* __restrict__ active, long long nTiles,
+                                                          int* __restrict__ units, int* __restrict__ count) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int c = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (long long t0 = 0; t0 < nTiles; t0 += blockDim.x) {
+    const long long t = t0 + threadIdx.x;
+    const bool live = t < nTiles && ((active[t] >> c) & 1u);
+    const unsigned int b = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (live) units[(long long)c * nTiles + off + __popc(b & ((1u << lane) - 1u))] = (int)t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) count[c] = s_base;
+}
+
+// gprefix[c] = number of groups of `warps` units before camera c; gprefix[C] = total
+__global__ void group_prefix_kernel(const int* __restrict__ count, int C, int warps, int* __restrict__ gprefix) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int c = 0; c < C; ++c) {
+      gprefix[c] = acc;
+      acc += (count[c] + warps - 1) / warps;
+    }
+    gprefix[C] = acc;
+  }
+}
+
+// one CTA per (tile, camera) unit: coalesced row loads -> shared -> coalesced [n][lane] stores
+__global__ void __launch_bounds__(256) tile_observations_kernel(const double2* __restrict__ ref,
+                                                                double2* __restrict__ tiled,
+                                                                const int* __restrict__ perm, int C, long long F,
+                                                                int N, long long nUnits) {
+  extern __shared__ double2 s_rows[];   // [32][N + 1]
+  const int ldr = N + 1;
+  for (long long unit = blockIdx.x; unit < nUnits; unit += gridDim.x) {
+    const long long tile = unit / C;
+    const int c = (int)(unit % C);
+    for (int i = threadIdx.x; i < kTile * N; i += blockDim.x) {
+      const int r = i / N, n = i % N;
+      const int f = perm[tile * kTile + r];
+      double2 v = make_double2(nan(""), nan(""));
+      if (f >= 0) v = ref[((long long)c * F + f) * N + n];
+      s_rows[r * ldr + n] = v;
+    }
+    __syncthreads();
+    double2* out = tiled + (size_t)unit * N * kTile;
+    for (int i = threadIdx.x; i < kTile * N; i += blockDim.x) out[i] = s_rows[(i % kTile) * ldr + i / kTile];
+    __syncthreads();
   }
 }
 
@@ -81,11 +180,37 @@ __global__ void count_rows_kernel(const double* __restrict__ ref, long long rows
 
 int launch_tile_observations(mcba_handle* h) {
   const Layout& L = h->L;
-  const long long total = L.nTiles * L.C * L.N * kTile;
-  int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-  tile_observations_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref),
-                                                       h->d_obs_tiled, L.C, L.F, L.N, L.nTiles);
-  h->launches++;
+  const int blocks = 148 * 8;
+  // ---- frame order: identity, or sorted by visibility mask
+  frame_mask_kernel<<<blocks, 256, 0, h->stream>>>(h->d_obs_ref, L.C, L.F, L.N, h->d_mask);
+  iota_kernel<<<blocks, 256, 0, h->stream>>>(h->d_perm, L.Fpad);
+  h->launches += 2;
+  static const bool no_sort = getenv("MCBA_NO_FRAME_SORT") != nullptr;
+  if (L.C <= 12 && !no_sort) {   // 2^C patterns: beyond that tiles would not share a mask anyway
+    size_t bytes = 0;
+    unsigned int* keys_out = h->d_mask + L.Fpad;
+    int* vals_out = h->d_perm + L.Fpad;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->d_mask, keys_out, h->d_perm, vals_out, (int)L.F, 0, L.C, h->stream);
+    if (bytes > h->sort_tmp_bytes) {
+      if (h->d_sort_tmp) cudaFree(h->d_sort_tmp);
+      MCBA_CUDA(cudaMalloc(&h->d_sort_tmp, bytes));
+      h->sort_tmp_bytes = bytes;
+    }
+    MCBA_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, bytes, h->d_mask, keys_out, h->d_perm, vals_out, (int)L.F,
+                                              0, L.C, h->stream));
+    MCBA_CUDA(cudaMemcpyAsync(h->d_perm, vals_out, sizeof(int) * L.F, cudaMemcpyDeviceToDevice, h->stream));
+    h->launches += 2;
+  }
+  tile_active_kernel<<<blocks, 256, 0, h->stream>>>(h->d_mask, h->d_perm, L.F, L.nTiles, h->d_active);
+  const long long units = L.nTiles * L.C;
+  const int grid = (int)(units < 148 * 8 ? units : 148 * 8);
+  tile_observations_kernel<<<grid, 256, sizeof(double2) * kTile * (L.N + 1), h->stream>>>(
+      reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obs_tiled, h->d_perm, L.C, L.F, L.N, units);
+  build_units_kernel<<<L.C, 256, 0, h->stream>>>(h->d_active, L.nTiles, h->d_units, h->d_unit_count);
+  group_prefix_kernel<<<1, 32, 0, h->stream>>>(h->d_unit_count, L.C, h->prod_warps, h->d_unit_count + 32);
+  // dead units are never written by K2p: their hand-off stays zero
+  MCBA_CUDA(cudaMemsetAsync(h->d_H, 0, sizeof(double) * (size_t)L.nTiles * L.C * 63 * kTile, h->stream));
+  h->launches += 4;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
 }
@@ -215,6 +340,7 @@ int launch_predict(mcba_handle* h, const double* x, double* uv_out) {
 // warp per (tile, camera), lane = frame, tiled SoA (same stream as K2a without the Jacobian)
 __global__ void __launch_bounds__(256) cost_kernel(const double* __restrict__ x, const double2* __restrict__ obs,
                                                    const double* __restrict__ obj, const CamConst* __restrict__ cams,
+                                                   const int* __restrict__ perm, const unsigned int* __restrict__ active,
                                                    int C, long long F, int N, long long nTiles, int loss, double inv_c,
                                                    double c2, double* __restrict__ part, unsigned int* __restrict__ counter,
                                                    double* __restrict__ out) {
@@ -230,8 +356,9 @@ __global__ void __launch_bounds__(256) cost_kernel(const double* __restrict__ x,
   for (long long job = gw; job < nTiles * C; job += nw) {
     const long long tile = job / C;
     const int c = (int)(job % C);
-    const long long f = tile * kTile + lane;
-    if (f < F) {
+    if (!((active[tile] >> c) & 1u)) continue;   // no observation of camera c in this tile
+    const long long f = perm[tile * kTile + lane];
+    if (f >= 0) {
       const CamConst& cam = cams[c];
       const Intr in{cam.fx, cam.fy, cam.cx, cam.cy, cam.k1, cam.k2};
       const double* ps = x + 12 * (long long)C + 6 * f;
@@ -313,7 +440,7 @@ int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, doubl
   double* part = h->d_scal + 64;                                  // [grid_cost][3]
   unsigned int* counter = reinterpret_cast<unsigned int*>(h->d_scal + 32);
   cost_kernel<<<h->grid_cost, 256, sizeof(double) * 3 * L.N, h->stream>>>(
-      x, h->d_obs_tiled, h->d_obj, h->d_cams, L.C, L.F, L.N, L.nTiles, loss, 1.0 / f_scale,
+      x, h->d_obs_tiled, h->d_obj, h->d_cams, h->d_perm, h->d_active, L.C, L.F, L.N, L.nTiles, loss, 1.0 / f_scale,
       f_scale * f_scale, part, counter, out_scal);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());

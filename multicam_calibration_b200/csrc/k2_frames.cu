@@ -24,6 +24,7 @@ struct K2CParams {
   int C;
   long long F, nTiles;
   const double* H;       // [tile][c][63][32]
+  const int* perm;       // tile slot -> frame index in x (-1 = padding)
   const double* x;       // 12C + 6F
   const CamConst* cams;
   double lambda;
@@ -155,8 +156,8 @@ __global__ void __launch_bounds__(kW * 32, 2) k2c_kernel(const K2CParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = p.C, nc = 12 * C;
   const long long tile = blockIdx.x;
-  const long long f = tile * kTile + lane;
-  const bool fvalid = f < p.F;
+  const long long f = p.perm[tile * kTile + lane];
+  const bool fvalid = f >= 0;
   double pose[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
@@ -266,8 +267,8 @@ __global__ void __launch_bounds__(kC * 32, 1) k2c_ring_kernel(const K2CParams p)
 
   for (int it = 0; it < n_it; ++it) {
     const long long tile = blockIdx.x + (long long)it * gridDim.x;
-    const long long f = tile * kTile + lane;
-    const bool fvalid = f < p.F;
+    const long long f = p.perm[tile * kTile + lane];
+    const bool fvalid = f >= 0;
     double pose[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
@@ -362,8 +363,11 @@ int launch_k2_producer(mcba_handle* h, const double* x, int loss, double f_scale
   p.N = L.N;
   p.F = L.F;
   p.nTiles = L.nTiles;
-  p.nGroups = (long long)L.C * ((L.nTiles + h->prod_warps - 1) / h->prod_warps);
   p.obs = h->d_obs_tiled;
+  p.perm = h->d_perm;
+  p.units = h->d_units;
+  p.unit_count = h->d_unit_count;
+  p.gprefix = h->d_unit_count + 32;
   p.obj = h->d_obj;
   p.x = x;
   p.cams = h->d_cams;
@@ -384,6 +388,7 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
   p.F = L.F;
   p.nTiles = L.nTiles;
   p.H = h->d_H;
+  p.perm = h->d_perm;
   p.x = x;
   p.cams = h->d_cams;
   p.lambda = lambda;

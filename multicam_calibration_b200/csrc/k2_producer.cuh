@@ -13,9 +13,10 @@
 //     per-frame Schur kernel K2c through the coalesced hand-off buffer H[tile][c][63][lane].
 // Nothing per-observation is written: algorithmic HBM traffic is 16 B/observation.
 //
-// Scheduling: units are ordered camera-major in groups of kWarps tiles; every CTA owns a
-// contiguous range of groups, so the camera index is CTA-uniform and changes at most a few times
-// per CTA.  All kWarps warps of the CTA walk corners (no consumer warps, no named barriers: the
+// Scheduling: only LIVE units (camera has observations in the tile; frames are sorted by
+// visibility mask, k1_residual.cu) are walked.  They are ordered camera-major in groups of kWarps
+// units; every CTA owns a contiguous, equally sized range of groups, so the camera index is
+// CTA-uniform and changes at most a few times per CTA.  All kWarps warps of the CTA walk corners (no consumer warps, no named barriers: the
 // per-frame Schur step is the separate kernel K2c).  The corner loop is ONE branch-free basic
 // block: missing observations are handled with selects, the reciprocal and rsqrt are inlined
 // Newton iterations on MUFU seeds (no slow-path calls), the loss is a template parameter.
@@ -30,8 +31,11 @@ namespace mcba {
 struct K2PParams {
   int C, N;
   long long F, nTiles;
-  long long nGroups;          // C * ceil(nTiles / kWarps)
   const double2* obs;         // tiled [tile][c][n][lane]
+  const int* perm;            // tile slot -> frame index in x (-1 = padding)
+  const int* units;           // [C][nTiles] live tiles per camera, compacted (build_units_kernel)
+  const int* unit_count;      // [C] live units per camera
+  const int* gprefix;         // [C + 1] groups of kWarps units before camera c; [C] = total
   const double* obj;          // (N,3)
   const double* x;            // 12C + 6F
   const CamConst* cams;       // per-camera constants (prep_cameras_kernel)
@@ -126,13 +130,39 @@ __device__ __forceinline__ void robust_weights_t(double f, bool valid, double in
   }
 }
 
+#ifndef MCBA_K2P_LAUNDER
+#define MCBA_K2P_LAUNDER 1
+#endif
+#ifndef MCBA_K2P_VOLATILE_SR
+#define MCBA_K2P_VOLATILE_SR 1
+#endif
+#if MCBA_K2P_VOLATILE_SR
+typedef const volatile double* SrPtr;
+#else
+typedef const double* __restrict__ SrPtr;
+#endif
+
+// The camera intrinsics reach the corner loop through an opaque FP64 add: uses inside the loop
+// then depend on a fixed-latency ALU result, not on the scoreboard of the global load that
+// fetched them before the loop.  (ptxas otherwise makes the first FP64 instruction of every
+// iteration wait on that scoreboard, which it shares with the in-loop observation prefetch:
+// 26 % of all stall samples in profiles/r01_b.)
+struct IntrReg {
+  double fx, fy, cx, cy, k1, k2;
+};
+__device__ __forceinline__ double opaque(double v) {
+#if MCBA_K2P_LAUNDER
+  asm volatile("add.f64 %0, %0, 0d0000000000000000;" : "+d"(v));
+#endif
+  return v;
+}
+
 // Shared part of the projection of one corner: camera-frame point, distortion, d(u,v)/d(x,y).
 struct Proj {
   double x, y, iz, r2, d, A00, A01, A10, A11, su, sv, pu, pv;
 };
 
-__device__ __forceinline__ void project_shared(const CamConst& cam, const double* __restrict__ sR, double qx,
-                                               double qy, double qz, Proj& o) {
+__device__ __forceinline__ void project_shared(const IntrReg& cam, SrPtr sR, double qx, double qy, double qz, Proj& o) {
   // sR: this lane's [Rcf (9) | tcf (3)], stride 32 doubles between entries
   const double X = fma(sR[0 * 32], qx, fma(sR[1 * 32], qy, fma(sR[2 * 32], qz, sR[9 * 32])));
   const double Y = fma(sR[3 * 32], qx, fma(sR[4 * 32], qy, fma(sR[5 * 32], qz, sR[10 * 32])));
@@ -156,7 +186,7 @@ __device__ __forceinline__ void project_shared(const CamConst& cam, const double
 
 // Raw Jacobian row of u (kU) or v: [d/df, d/dc = 1, d/dk1, d/dk2, m (3), G (3)]  (mcba_obs.cuh).
 template <bool kU>
-__device__ __forceinline__ void jac_row(const CamConst& cam, const Proj& p, double (&a)[10]) {
+__device__ __forceinline__ void jac_row(const IntrReg& cam, const Proj& p, double (&a)[10]) {
   const double f = kU ? cam.fx : cam.fy, w = kU ? p.x : p.y;
   const double Aa = kU ? p.A00 : p.A10, Ab = kU ? p.A01 : p.A11, s = kU ? p.su : p.sv;
   a[0] = w * p.d;
@@ -173,7 +203,7 @@ __device__ __forceinline__ void jac_row(const CamConst& cam, const Proj& p, doub
 
 // One unit (camera, 32 frames): walk the N corners, both rows of each observation.
 template <int kLoss>
-__device__ __forceinline__ void walk_corners(const K2PParams& p, const CamConst& cam, const double* __restrict__ sR,
+__device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& cam, SrPtr sR,
                                              const double2* __restrict__ ob, const double* __restrict__ s_obj,
                                              double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
                                              double& cnt_acc) {
@@ -225,20 +255,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
   for (int i = threadIdx.x; i < C * kAcc; i += blockDim.x) s_U[i] = 0.0;
   double cost_acc = 0.0, sumsq_acc = 0.0, cnt_acc = 0.0;
   double* sR = s_R + (size_t)warp * 12 * 32 + lane;
-  const long long tileBlocks = (p.nTiles + kWarps - 1) / kWarps;
   __syncthreads();
 
-  // contiguous range of camera-major groups for this CTA
-  const long long g_begin = (p.nGroups * blockIdx.x) / gridDim.x;
-  const long long g_end = (p.nGroups * (blockIdx.x + 1)) / gridDim.x;
-  for (long long g = g_begin; g < g_end; ++g) {
-    const int c = (int)(g / tileBlocks);                // CTA-uniform
-    const long long tile = (g % tileBlocks) * kWarps + warp;
+  // contiguous range of camera-major groups of live units for this CTA (all CTAs get the same
+  // number of fully populated groups: static, balanced, and the partial sums stay deterministic)
+  const int nGroups = p.gprefix[C];
+  const int g_begin = (int)(((long long)nGroups * blockIdx.x) / gridDim.x);
+  const int g_end = (int)(((long long)nGroups * (blockIdx.x + 1)) / gridDim.x);
+  int c = 0;
+  for (int g = g_begin; g < g_end; ++g) {
+    while (c + 1 < C && p.gprefix[c + 1] <= g) ++c;     // CTA-uniform
+    const int k = (g - p.gprefix[c]) * kWarps + warp;
+    const bool live = k < p.unit_count[c];
+    const long long tile = live ? p.units[(long long)c * p.nTiles + k] : 0;
     const CamConst& cam = p.cams[c];
     double* uw = s_Uw + warp * kAcc;
-    if (tile < p.nTiles) {
-      const long long f = tile * kTile + lane;
-      const bool fvalid = f < p.F;
+    if (live) {
+      const long long f = p.perm[tile * kTile + lane];
+      const bool fvalid = f >= 0;
       {
         double pose[6];
 #pragma unroll
@@ -258,7 +292,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
       double acc[kAcc];
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
-      walk_corners<kLoss>(p, cam, sR, ob, s_obj, acc, cost_acc, sumsq_acc, cnt_acc);
+      const IntrReg in{opaque(cam.fx), opaque(cam.fy), opaque(cam.cx), opaque(cam.cy), opaque(cam.k1), opaque(cam.k2)};
+      walk_corners<kLoss>(p, in, sR, ob, s_obj, acc, cost_acc, sumsq_acc, cnt_acc);
       uw[lane] = lane_transpose_sum32<0>(acc, lane);
       uw[32 + lane] = lane_transpose_sum32<32>(acc, lane);
       uw[64 + lane] = lane_transpose_sum32<64>(acc, lane);

@@ -472,6 +472,7 @@ struct BackParams {
   int C, nc, rank;
   long long F, nTiles;
   const CamConst* cams;
+  const int* perm;      // tile slot -> frame index in x (-1 = padding)
   const double* x;
   double* x_new;
   const double* dcam;   // true-basis camera step (12C)
@@ -511,8 +512,8 @@ __global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackPara
 #pragma unroll
     for (int k = 0; k < 6; ++k) sv[(warp * 6 + k) * 32 + lane] = s[k];
     __syncthreads();
-    const long long f = tile * kTile + lane;
-    if (warp == 0 && f < p.F) {
+    const long long f = p.perm[tile * kTile + lane];
+    if (warp == 0 && f >= 0) {
       double v[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
@@ -596,7 +597,7 @@ int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda
   const Layout& L = h->L;
   BackParams p;
   p.C = L.C; p.nc = L.nc; p.rank = h->rank; p.F = L.F; p.nTiles = L.nTiles;
-  p.cams = h->d_cams; p.x = x; p.x_new = x_new; p.dcam = h->d_dcam;
+  p.cams = h->d_cams; p.perm = h->d_perm; p.x = x; p.x_new = x_new; p.dcam = h->d_dcam;
   p.Z = h->d_Z; p.Linv = h->d_Linv; p.y = h->d_y; p.gpose = h->d_gpose; p.D2pose = h->d_D2pose;
   p.D2cam = h->d_D2cam; p.gcam = h->d_red + L.offG;
   p.part = h->d_scal + 64 + 3 * 4096;                                     // [grid_back][4]

@@ -47,6 +47,13 @@ struct mcba_handle {
   double* d_obs_ref = nullptr;   // (C,F,N,2) reference layout
   double2* d_obs_tiled = nullptr;
   double* d_obj = nullptr;
+  int* d_perm = nullptr;             // [2 Fpad] tile slot -> frame (-1 padding) | sort scratch
+  unsigned int* d_mask = nullptr;    // [2 Fpad] ~visibility mask per frame | sort scratch
+  unsigned int* d_active = nullptr;  // [nTiles] cameras with at least one observation in the tile
+  int* d_units = nullptr;            // [C][nTiles] live tiles per camera, compacted
+  int* d_unit_count = nullptr;       // [0..C) live units per camera | [32..32+C] group prefix for K2p
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
   long long* d_row_off = nullptr;  // (C*F + 1) exclusive scan of finite scalars per (c,f)
   long long m = 0;                 // finite scalar residuals
   long long n_obs = 0;             // (c,f,n) with at least one finite scalar
