@@ -214,10 +214,13 @@ __global__ void __launch_bounds__(kW * 32, 2) k2c_kernel(const K2CParams p) {
   }
 }
 
-// Ring path (kC <= 6 cameras, warp = camera): persistent CTAs, the whole hand-off block of a tile
-// (kC x 63 x 32 doubles, contiguous) arrives by ONE bulk async copy into a 2-stage shared-memory
-// ring while the previous tile is being processed, so no warp ever waits on a global load; Z, y and
-// L^-1 leave as coalesced 256-byte rows.  Partial outputs (Z y, max |g|) per CTA.
+// Staged path (kC <= 6 cameras, warp = camera): persistent CTAs, two per SM.  The whole hand-off
+// block of a tile (kC x 63 x 32 doubles, contiguous) arrives by ONE bulk async copy into shared
+// memory; while one CTA of the SM waits for its copy the other one computes, so no warp waits on
+// a global load and each scheduler hosts three warps.  Z, y and L^-1 leave as coalesced 256-byte
+// rows.  The cross-camera sum of the pose block goes through a small exchange buffer in two
+// rounds (11 + 10 values; g'' travels in the camera's already consumed q_ext slots of the
+// stage), which is what lets two CTAs fit in the 228 KB of an SM.  Partial outputs per CTA.
 __device__ __forceinline__ unsigned k2c_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void k2c_mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
@@ -231,13 +234,15 @@ __device__ __forceinline__ void k2c_mbar_wait(unsigned long long* bar, unsigned 
       "}\n" ::"r"(k2c_smem_u32(bar)), "r"(parity) : "memory");
 }
 
+constexpr int kXchg = 11;   // values per exchange round
+
 template <int kC>
-__global__ void __launch_bounds__(kC * 32, 1) k2c_ring_kernel(const K2CParams p) {
+__global__ void __launch_bounds__(kC * 32, 2) k2c_ring_kernel(const K2CParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ unsigned long long full_bar[2];
+  __shared__ unsigned long long full_bar;
   constexpr int kStage = kC * kHandoff * kTile;                  // doubles per stage
-  double* stages = reinterpret_cast<double*>(smem_raw);          // [2][kC][63][32]
-  double* s_V = stages + 2 * kStage;                             // [kC][21][32]
+  double* stage = reinterpret_cast<double*>(smem_raw);           // [kC][63][32]
+  double* s_X = stage + kStage;                                  // [kC][kXchg][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nc = 12 * kC;
   const int c = warp;
@@ -245,25 +250,23 @@ __global__ void __launch_bounds__(kC * 32, 1) k2c_ring_kernel(const K2CParams p)
   auto issue = [&](int it) {   // thread 0 only
     const long long tile = blockIdx.x + (long long)it * gridDim.x;
     const unsigned bytes = kStage * sizeof(double);
-    unsigned long long* bar = &full_bar[it & 1];
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2c_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2c_smem_u32(&full_bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     k2c_smem_u32(stages + (size_t)(it & 1) * kStage)),
-                 "l"(p.H + (size_t)tile * kStage), "r"(bytes), "r"(k2c_smem_u32(bar))
+                     k2c_smem_u32(stage)),
+                 "l"(p.H + (size_t)tile * kStage), "r"(bytes), "r"(k2c_smem_u32(&full_bar))
                  : "memory");
   };
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(&full_bar[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(&full_bar[1])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(&full_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (n_it > 0) issue(0);
-    if (n_it > 1) issue(1);
   }
   __syncthreads();
   const CamConst& cam = p.cams[c];
   double zy[12], gmax = 0.0;
 #pragma unroll
   for (int i = 0; i < 12; ++i) zy[i] = 0.0;
+  double* h = stage + (size_t)c * kHandoff * kTile + lane;
 
   for (int it = 0; it < n_it; ++it) {
     const long long tile = blockIdx.x + (long long)it * gridDim.x;
@@ -275,39 +278,55 @@ __global__ void __launch_bounds__(kC * 32, 1) k2c_ring_kernel(const K2CParams p)
     double Jl[9], Rc[9], K[9];
     so3_left_jacobian(pose, Jl);
     pose_map(cam, pose, Rc, K);
-    k2c_mbar_wait(&full_bar[it & 1], (unsigned)((it >> 1) & 1));
-    double* h = stages + (size_t)(it & 1) * kStage + (size_t)c * kHandoff * kTile + lane;
+    k2c_mbar_wait(&full_bar, (unsigned)(it & 1));
     double Vpp[21], gpp[6];
+    {
+      double Vp[21], gq[6];
 #pragma unroll
-    for (int i = 0; i < 21; ++i) Vpp[i] = 0.0;
+      for (int i = 0; i < 21; ++i) Vp[i] = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) gpp[i] = 0.0;
-    pose_block_add(h, Rc, K, Vpp, gpp);
-    // exchange: V'' through s_V, g'' through this camera's (already consumed) q_ext slots of the stage
+      for (int i = 0; i < 6; ++i) gq[i] = 0.0;
+      pose_block_add(h, Rc, K, Vp, gq);
+      // round 1: V''[0..10] through s_X, g'' through this camera's (consumed) q_ext slots
 #pragma unroll
-    for (int i = 0; i < 21; ++i) s_V[(c * 21 + i) * kTile + lane] = Vpp[i];
+      for (int i = 0; i < kXchg; ++i) s_X[(c * kXchg + i) * kTile + lane] = Vp[i];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) h[(57 + i) * kTile] = gpp[i];
-    __syncthreads();
+      for (int i = 0; i < 6; ++i) h[(57 + i) * kTile] = gq[i];
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 21; ++i) Vpp[i] = 0.0;
+      for (int i = 0; i < kXchg; ++i) {
+        double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) gpp[i] = 0.0;
-    const double* hq = stages + (size_t)(it & 1) * kStage + lane;
+        for (int w = 0; w < kC; ++w) t += s_X[(w * kXchg + i) * kTile + lane];
+        Vpp[i] = t;
+      }
 #pragma unroll
-    for (int w = 0; w < kC; ++w) {
+      for (int i = 0; i < 6; ++i) {
+        double t = 0.0;
 #pragma unroll
-      for (int i = 0; i < 21; ++i) Vpp[i] += s_V[(w * 21 + i) * kTile + lane];
+        for (int w = 0; w < kC; ++w) t += stage[((size_t)w * kHandoff + 57 + i) * kTile + lane];
+        gpp[i] = t;
+      }
+      __syncthreads();
+      // round 2: V''[11..20]
 #pragma unroll
-      for (int i = 0; i < 6; ++i) gpp[i] += hq[((size_t)w * kHandoff + 57 + i) * kTile];
+      for (int i = kXchg; i < 21; ++i) s_X[(c * kXchg + i - kXchg) * kTile + lane] = Vp[i];
+      __syncthreads();
+#pragma unroll
+      for (int i = kXchg; i < 21; ++i) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kC; ++w) t += s_X[(w * kXchg + i - kXchg) * kTile + lane];
+        Vpp[i] = t;
+      }
     }
     double Linv[21], yv[6], gp[6];
     pose_block_factor(Vpp, gpp, Jl, p.lambda, p.D2pose + (size_t)tile * 6 * 32 + lane, warp == 0, Linv, yv, gp, gmax);
     if (warp == 0) store_pose_outputs(p, tile, f, fvalid, lane, Linv, yv, gp);
     z_rows(h, Rc, K, Jl, Linv, yv, p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane, zy);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic writes (g'') precede the next bulk copy
-    __syncthreads();   // every warp is done with this stage and with s_V
-    if (threadIdx.x == 0 && it + 2 < n_it) issue(it + 2);
+    __syncthreads();   // every warp is done with the stage and with s_X
+    if (threadIdx.x == 0 && it + 1 < n_it) issue(it + 1);
   }
   const double v = zy_lane_sum(zy, lane);
   if (lane < 12) p.partZy[(size_t)blockIdx.x * nc + c * 12 + lane] = v;
@@ -323,7 +342,7 @@ __global__ void __launch_bounds__(kC * 32, 1) k2c_ring_kernel(const K2CParams p)
 int k2_consumer_parts(const Layout& L, int n_sm, bool* ring) {
   static const bool no_ring = getenv("MCBA_K2C_GENERAL") != nullptr;   // debugging: force the general path
   *ring = !no_ring && L.C >= 2 && L.C <= 6;
-  return *ring ? (int)(L.nTiles < n_sm ? L.nTiles : n_sm) : (int)L.nTiles;
+  return *ring ? (int)(L.nTiles < 2 * n_sm ? L.nTiles : 2 * n_sm) : (int)L.nTiles;
 }
 
 int k2_producer_grid(const Layout& L, int n_sm, int* warps) {
@@ -401,7 +420,7 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
   p.partZy = h->d_partZy;
   if (h->k2c_ring) {
     const int C = L.C;
-    const size_t smem = sizeof(double) * ((size_t)2 * C * kHandoff * kTile + (size_t)C * 21 * kTile);
+    const size_t smem = sizeof(double) * ((size_t)C * kHandoff * kTile + (size_t)C * kXchg * kTile);
     const int grid = h->n_part_c;
 #define MCBA_K2C_RING(CV)                                                                                          \
   do {                                                                                                             \
