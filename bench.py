@@ -4,6 +4,8 @@
     python bench.py --gpus N --steps K --warmup W            # this engine (B200)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
 
+The metric is BASELINE.json's: observations/s through residual + analytic Jacobian + Schur
+accumulation (`value`, `e2e`), with the BA time-to-converge on the same data in `ba_converge`.
 A "step" is one pass of residual + analytic Jacobian + Schur accumulation (the
 reduced camera system S, b) over every observation of the workload:
 6 cameras x 50,000 frames x 35 corners per GPU, 20 % missing detections, 0.5 px
@@ -24,12 +26,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "obs/s residual+Jacobian+Schur"
+METRIC = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")))["metric"] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "BASELINE.json")) \
+    else "obs/s residual+Jacobian+Schur; BA time-to-converge, 6 cams\u00d750k frames"
 UNIT = "obs/s"
 CAMS, FRAMES, SIGMA, P_MISSING = 6, 50_000, 0.5, 0.2
 WORKLOAD = (f"{CAMS} cams x {FRAMES} frames/GPU x 35 corners, {int(P_MISSING * 100)}% missing detections, "
             f"sigma={SIGMA} px (BASELINE.json configs[2])")
 CPU_SAMPLE_FRAMES = 1000
+ALG_FMA_PER_OBS = 250.0   # projection + Jacobian rows ~65, robust weights ~30, A_cf / q_cf accumulation ~150, bookkeeping ~5
 
 
 def measured_peaks():
@@ -287,6 +292,9 @@ def run_engine(args):
     else:
         ba_ms, n_obs_total, launches_total = res.solve_ms, n_obs_local, launches
 
+    fp64_peak = ctypes.c_double(0.0)
+    if rank == 0:
+        _native.check(lib.mcba_measure_fp64_peak(local, ctypes.byref(fp64_peak)))
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         ms_step = ms / args.steps
@@ -296,6 +304,8 @@ def run_engine(args):
         syrk_ms = kms[2] / max(kn.value, 1)
         alg_bytes = 16.0 * n_obs_local + 48.0 * frames          # 16 B/obs + 48 B/frame (rank 0's launch)
         achieved = alg_bytes / (k2_ms * 1e-3) / 1e9
+        # FP64 ceiling of the same kernel: ALG_FMA_PER_OBS fused multiply-adds per observation
+        fma_rate = ALG_FMA_PER_OBS * n_obs_local / (k2_ms * 1e-3)
         traffic = None
         prof_json = os.path.join(ROOT, "profiles", "k2_frames_traffic.json")
         if os.path.exists(prof_json):
@@ -306,15 +316,20 @@ def run_engine(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu": frames, "observations_total": n_obs_total,
                        "sharding": f"frames x{world}, one NCCL all-reduce of the packed reduced camera system per step",
-                       "l2": "inputs (168 MB observations + 173 MB Z written) exceed the 126 MB L2; no flush needed",
+                       "l2": "per step 168 MB of observations are read, 151 MB of hand-off and 173 MB of Z are written and "
+                             "re-read: the working set exceeds the 126 MB L2, no flush needed",
                        "loss": "soft_l1", "lambda": lam},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k2p_kernel (residual + analytic Jacobian + robust weights + A_cf accumulation)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k2_ms,
-                         "note": "fp64 kernel at ~1e3 flop/obs is FP64-pipe bound, not HBM bound (DESIGN.md); "
-                                 "see profiles/ for sm__pipe_fp64 utilisation"},
+                         "fp64_pipe": {"achieved": fma_rate * 2e-12, "peak": fp64_peak.value * 2e-12, "unit": "TFLOP/s",
+                                       "frac": fma_rate / fp64_peak.value if fp64_peak.value else None,
+                                       "fma_per_obs": ALG_FMA_PER_OBS,
+                                       "peak_source": "DFMA loop timed in this run (mcba_measure_fp64_peak)"},
+                         "note": "the kernel does ~250 FP64 FMAs per 16-byte observation: it is bound by the FP64 "
+                                 "pipe (fp64_pipe.frac), not by HBM; frac is the HBM figure the contract asks for"},
             "kernels_ms": {"k2p_corner_walk": k2_ms, "k2c_frame_schur": k2c_ms, "k2_syrk": syrk_ms,
                            "finalize_allreduce": kms[3] / max(kn.value, 1)},
             "e2e": {"value": n_obs_total / (e2e_ms / e2e_steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,

@@ -170,6 +170,10 @@ int mcba_triangulate(int device, void* cuda_stream, const double* d_uvs, int n_c
  * counters and switches recording on/off. */
 int mcba_profile(mcba_handle* h, int enable, double* ms_out, int* n_out);
 
+/* FP64 vector-pipe peak of the device, measured with a dependency-free DFMA loop (fused
+ * multiply-adds per second): the compute ceiling bench.py quotes beside the HBM roofline. */
+int mcba_measure_fp64_peak(int device, double* fma_per_s);
+
 /* Number of kernels this handle has launched (bench.py gpu_launches). */
 int64_t mcba_kernel_launches(mcba_handle* h);
 

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "mcba_triangulate": (_I, [_I, _P, _P, _I, _L, _P, _P, _P, _P]),
     "mcba_kernel_launches": (_L, [_P]),
     "mcba_profile": (_I, [_P, _I, ctypes.POINTER(_D), ctypes.POINTER(_I)]),
+    "mcba_measure_fp64_peak": (_I, [_I, ctypes.POINTER(_D)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -410,7 +410,7 @@ int launch_finalize(mcba_handle* h) {
     // d_Sraw = [S (nc8^2) | U (C kAcc) | Z y (nc)]
     const ReduceSeg s0{h->d_partSyrk, h->grid_syrk, lenS};
     const ReduceSeg s1{h->d_partU, h->grid_frames, lenU};
-    reduce_partials_kernel<64, 4><<<(lenS + lenU + 63) / 64, 256, 0, h->stream>>>(s0, s1, h->d_Sraw);
+    reduce_partials_kernel<16, 16><<<(lenS + lenU + 15) / 16, 256, 0, h->stream>>>(s0, s1, h->d_Sraw);
     const ReduceSeg z0{h->d_partZy, h->n_part_c, lenZy};
     const ReduceSeg z1{nullptr, 0, 0};
     reduce_partials_kernel<8, 32><<<(lenZy + 7) / 8, 256, 0, h->stream>>>(z0, z1, h->d_Sraw + lenS + lenU);

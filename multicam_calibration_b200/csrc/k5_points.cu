@@ -311,3 +311,54 @@ int mcba_triangulate(int device, void* stream, const double* d_uvs, int C, int64
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- FP64 pipe peak (bench.py roofline denominator)
+// Dependent-chain-free DFMA loop, 16 independent accumulators per thread, 16 warps per SM:
+// the same measurement as scripts/ubench/fp64_pipes.cu (mode 0), taken live on the device the
+// benchmark runs on.  Returns fused multiply-adds per second.
+namespace mcba {
+__global__ void __launch_bounds__(512) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a[16];
+  const double x = seed, y = 1.0 - 1e-9;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], y, x);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678) *out = s;
+}
+}  // namespace mcba
+
+extern "C" int mcba_measure_fp64_peak(int device, double* fma_per_s) {
+  using namespace mcba;
+  if (!fma_per_s) return MCBA_ERR_ARG;
+  MCBA_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MCBA_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  MCBA_CUDA(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  MCBA_CUDA(cudaEventCreate(&e0));
+  MCBA_CUDA(cudaEventCreate(&e1));
+  const int iters = 20000, grid = prop.multiProcessorCount;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    MCBA_CUDA(cudaEventRecord(e0));
+    fp64_peak_kernel<<<grid, 512>>>(d, iters, 0.5);
+    MCBA_CUDA(cudaEventRecord(e1));
+    MCBA_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MCBA_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double rate = (double)grid * 512 * 16 * (double)iters / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *fma_per_s = best;
+  return MCBA_OK;
+}

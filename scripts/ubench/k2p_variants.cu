@@ -125,13 +125,27 @@ int main(int argc, char** argv) {
   cudaMemcpy(d_cams, cams.data(), sizeof(CamConst) * 32, cudaMemcpyHostToDevice);
   cudaMemset(d_H, 0, Hn * 8);
 
+  // identity frame order, every (tile, camera) unit live, groups of 8 / 4 warps
+  std::vector<int> perm(nTiles * 32), units((size_t)C * nTiles), ucount(128, 0);
+  for (long long i = 0; i < nTiles * 32; ++i) perm[i] = i < F ? (int)i : -1;
+  for (int c = 0; c < C; ++c) { for (long long t = 0; t < nTiles; ++t) units[(size_t)c * nTiles + t] = (int)t; ucount[c] = (int)nTiles; }
+  int *d_perm, *d_units, *d_ucount;
+  cudaMalloc(&d_perm, perm.size() * 4); cudaMalloc(&d_units, units.size() * 4); cudaMalloc(&d_ucount, 128 * 4);
+  cudaMemcpy(d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_units, units.data(), units.size() * 4, cudaMemcpyHostToDevice);
+  auto set_groups = [&](int warps) {
+    int acc = 0;
+    for (int c = 0; c < C; ++c) { ucount[32 + c] = acc; acc += (int)((nTiles + warps - 1) / warps); }
+    ucount[32 + C] = acc;
+    cudaMemcpy(d_ucount, ucount.data(), 128 * 4, cudaMemcpyHostToDevice);
+  };
   K2PParams p;
+  p.perm = d_perm; p.units = d_units; p.unit_count = d_ucount; p.gprefix = d_ucount + 32;
   p.C = C; p.N = N; p.F = F; p.nTiles = nTiles;
   p.obs = reinterpret_cast<const double2*>(d_obs); p.obj = d_obj; p.x = d_x; p.cams = d_cams; p.inv_c = 1.0; p.c2 = 1.0;
   p.H = d_H; p.partU = d_partU; p.partS = d_partS;
 
   std::vector<double> H0, U0, H1, U1;
-  auto groups = [&](int warps) { return (long long)C * ((nTiles + warps - 1) / warps); };
   auto usum = [&](const std::vector<double>& U) {   // sum partials over CTAs -> C*96
     std::vector<double> s(C * kAcc, 0.0);
     for (int b = 0; b < grid; ++b) for (int i = 0; i < C * kAcc; ++i) s[i] += U[(size_t)b * C * kAcc + i];
@@ -142,11 +156,11 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < a.size(); ++i) { mx = fmax(mx, fabs(a[i] - b[i])); ref = fmax(ref, fabs(a[i])); }
     printf("    %s: max |diff| %.3e  (max |ref| %.3e, rel %.2e)\n", what, mx, ref, mx / ref);
   };
-  p.nGroups = groups(8);
+  set_groups(8);
   run_variant<kLossSoftL1, 8>("soft_l1, 8 warps", p, grid, H0, U0, Hn, Un, n_obs);
   run_variant<kLossSoftL1 | kLossIrls, 8>("soft_l1 IRLS weights, 8 warps", p, grid, H1, U1, Hn, Un, n_obs);
   run_variant<kLossLinear, 8>("linear, 8 warps", p, grid, H1, U1, Hn, Un, n_obs);
-  p.nGroups = groups(4);
+  set_groups(4);
   run_variant<kLossSoftL1, 4>("soft_l1, 4 warps", p, grid, H1, U1, Hn, Un, n_obs);
   cmp("H  4 warps vs 8 warps", H0, H1);
   cmp("U  4 warps vs 8 warps", usum(U0), usum(U1));
