@@ -222,10 +222,10 @@ def run_engine(args):
 
         for _ in range(args.warmup):
             step()
-        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None     # NVML start-up must not skew rank 0 against the others
         _native.check(lib.mcba_profile(h, 1, None, None))
         launches0 = prob.kernel_launches
-        sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(prob.stream)
         for _ in range(args.steps):
