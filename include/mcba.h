@@ -146,6 +146,23 @@ int mcba_gradient(mcba_handle* h, double* d_grad);
 int mcba_comm_unique_id(void* id128);
 int mcba_comm_init(mcba_handle* h, const void* id128, int rank, int nranks);
 
+/* Front end of bundle_adjust on the device (bundle_adjustment.py:265-285): frame eligibility
+ * (> 1 camera with a complete detection, :266), per-point reprojection errors of the initial
+ * guess on eligible frames (:269-276), worst per-camera mean error per frame (:279), outlier
+ * threshold (outlier_threshold, or 5 * nanmedian(err) when it is NaN, :281-282) and exclusion
+ * (:284-285).  d_uvs (C,F,N,2), d_obj (N,3), d_x = 12C camera parameters + 6F poses of ALL
+ * frames (device).  d_use (F bytes, device) receives 1 for every kept frame; h_stats[4] (host) =
+ * {threshold used, eligible frames, frames excluded as outliers, finite error values}.
+ * The random sub-sampling of :293-296 stays with the caller (numpy's global RNG). */
+int mcba_select_frames(int device, void* cuda_stream, const double* d_uvs, int n_cameras,
+                       int64_t n_frames, int n_points, const double* d_obj, const double* d_x,
+                       double outlier_threshold, uint8_t* d_use, double* h_stats);
+/* all_calib_uvs[:, use_frames] (bundle_adjustment.py:299-312) on the device:
+ * d_out (C, n_used, N, 2) = d_uvs (C, F, N, 2)[:, d_idx]. */
+int mcba_gather_frames(int device, void* cuda_stream, const double* d_uvs, int n_cameras,
+                       int64_t n_frames, int n_points, const int64_t* d_idx, int64_t n_used,
+                       double* d_out);
+
 /* geometry.py:277-325 project_points for P points and one camera:
  * d_points (P,3), ext (6), K (3x3 row major, skew honoured), dist (k1,k2) or NULL. */
 int mcba_project_points(int device, void* cuda_stream, const double* d_points, int64_t n_points,

@@ -75,6 +75,8 @@ _SIGNATURES = {
     "mcba_kernel_launches": (_L, [_P]),
     "mcba_profile": (_I, [_P, _I, ctypes.POINTER(_D), ctypes.POINTER(_I)]),
     "mcba_measure_fp64_peak": (_I, [_I, ctypes.POINTER(_D)]),
+    "mcba_select_frames": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _D, _P, ctypes.POINTER(_D)]),
+    "mcba_gather_frames": (_I, [_I, _P, _P, _I, _L, _I, _P, _L, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

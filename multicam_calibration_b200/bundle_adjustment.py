@@ -107,25 +107,57 @@ def bundle_adjustment_sparsity(all_calib_uvs):
     return A.tolil()
 
 
+def _select_frames_device(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
+                          n_frames, outlier_threshold):
+    """Device front end: returns ``(use_frames, d_uvs)`` with the full observation array left on
+    the GPU so that the kept frames can be gathered there."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    dev = torch.cuda.current_device()
+    uvs = np.ascontiguousarray(all_calib_uvs, dtype=np.float64)
+    C, F, N, _ = uvs.shape
+    x_all = serialize_params(all_extrinsics, all_intrinsics, calib_poses)
+    d_uvs = torch.as_tensor(uvs).to(f"cuda:{dev}")
+    d_x = torch.as_tensor(np.ascontiguousarray(x_all, dtype=np.float64)).to(f"cuda:{dev}")
+    d_obj = torch.as_tensor(np.ascontiguousarray(calib_objpoints, dtype=np.float64)).to(f"cuda:{dev}")
+    d_use = torch.empty(F, dtype=torch.uint8, device=f"cuda:{dev}")
+    stats = (ctypes.c_double * 4)()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    thr = float("nan") if outlier_threshold is None else float(outlier_threshold)
+    check(lib.mcba_select_frames(dev, stream, ctypes.c_void_p(d_uvs.data_ptr()), C, F, N,
+                                 ctypes.c_void_p(d_obj.data_ptr()), ctypes.c_void_p(d_x.data_ptr()), thr,
+                                 ctypes.c_void_p(d_use.data_ptr()), stats))
+    use_frames = torch.nonzero(d_use).ravel().cpu().numpy()
+    threshold = outlier_threshold if outlier_threshold is not None else stats[0]
+    print(f"Excluding {int(stats[2])} out of {len(use_frames)} frames "
+          f"based on an outlier threshold of {threshold}")
+    if not (n_frames is None or n_frames > len(use_frames)):
+        use_frames = np.random.choice(use_frames, n_frames, replace=False)
+    return use_frames, d_uvs
+
+
 def select_frames(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
                   n_frames=10000, outlier_threshold=None):
     """Frame eligibility, outlier rejection and sub-sampling of
-    bundle_adjustment.py:265-296 (same prints, same use of the global numpy RNG)."""
-    use_frames = np.nonzero((~np.isnan(all_calib_uvs).any((-1, -2))).sum(0) > 1)[0]
-    predicted = predict_calib_uvs(all_extrinsics, all_intrinsics, calib_objpoints, calib_poses[use_frames])
-    err = np.linalg.norm(all_calib_uvs[:, use_frames] - predicted, axis=-1)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", category=RuntimeWarning)
-        worst_mean_err = np.nanmax(np.nanmean(err, axis=-1), axis=0)
-    if outlier_threshold is None:
-        outlier_threshold = 5 * np.nanmedian(err)
-    exclude = np.nan_to_num(worst_mean_err) > outlier_threshold
-    use_frames = use_frames[~exclude]
-    print(f"Excluding {int(exclude.sum())} out of {len(use_frames)} frames "
-          f"based on an outlier threshold of {outlier_threshold}")
-    if not (n_frames is None or n_frames > len(use_frames)):
-        use_frames = np.random.choice(use_frames, n_frames, replace=False)
-    return use_frames
+    bundle_adjustment.py:265-296 (same rule, same print, same use of the global numpy RNG);
+    the statistics run on the device (``mcba_select_frames``)."""
+    return _select_frames_device(np.asarray(all_calib_uvs, dtype=np.float64), all_extrinsics, all_intrinsics,
+                                 np.asarray(calib_objpoints, dtype=np.float64),
+                                 np.asarray(calib_poses, dtype=np.float64), n_frames, outlier_threshold)[0]
+
+
+def _gather_frames_device(d_uvs, use_frames):
+    """``all_calib_uvs[:, use_frames]`` on the device."""
+    torch = _native.require_cuda()
+    lib = _native.load()
+    dev = d_uvs.device.index
+    C, F, N, _ = d_uvs.shape
+    d_idx = torch.as_tensor(np.ascontiguousarray(use_frames, dtype=np.int64)).to(d_uvs.device)
+    out = torch.empty((C, len(use_frames), N, 2), dtype=torch.float64, device=d_uvs.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.mcba_gather_frames(dev, stream, ctypes.c_void_p(d_uvs.data_ptr()), C, F, N,
+                                 ctypes.c_void_p(d_idx.data_ptr()), len(use_frames), ctypes.c_void_p(out.data_ptr())))
+    return out
 
 
 def bundle_adjust(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
@@ -144,13 +176,15 @@ def bundle_adjust(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints
     calib_poses = np.asarray(calib_poses, dtype=np.float64)
     calib_objpoints = np.asarray(calib_objpoints, dtype=np.float64)
     n_cameras = all_calib_uvs.shape[0]
-    use_frames = select_frames(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
-                               calib_poses, n_frames, outlier_threshold)
+    use_frames, d_uvs = _select_frames_device(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
+                                              calib_poses, n_frames, outlier_threshold)
     x0 = serialize_params(all_extrinsics, all_intrinsics, calib_poses[use_frames])
     if distributed.world_size() > 1:
+        del d_uvs
         x, result = distributed.solve_sharded(all_calib_uvs[:, use_frames], calib_objpoints, x0, **opt_kwargs)
     else:
-        prob = BAProblem(all_calib_uvs[:, use_frames], calib_objpoints)
+        prob = BAProblem(_gather_frames_device(d_uvs, use_frames), calib_objpoints)
+        del d_uvs
         try:
             x, result = prob.solve(x0, **opt_kwargs)
         finally:

@@ -99,11 +99,12 @@ class BAProblem:
         torch = _native.require_cuda()
         self.torch = torch
         self.lib = _native.load()
-        uvs = np.ascontiguousarray(all_calib_uvs, dtype=np.float64)
+        on_device = hasattr(all_calib_uvs, "is_cuda")     # a float64 CUDA tensor: no host round trip
+        uvs = all_calib_uvs if on_device else np.ascontiguousarray(all_calib_uvs, dtype=np.float64)
         obj = np.ascontiguousarray(calib_objpoints, dtype=np.float64)
         if uvs.ndim != 4 or uvs.shape[-1] != 2 or obj.shape != (uvs.shape[2], 3):
             raise ValueError("all_calib_uvs must be (C,F,N,2) and calib_objpoints (N,3)")
-        self.C, self.F, self.N, _ = uvs.shape
+        self.C, self.F, self.N, _ = (int(v) for v in uvs.shape)
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.n_params = 12 * self.C + 6 * self.F
         self._h = ctypes.c_void_p()
@@ -146,13 +147,24 @@ class BAProblem:
 
     @_on_stream
     def set_observations(self, uvs, obj=None):
-        uvs = np.ascontiguousarray(uvs, dtype=np.float64)
-        if uvs.shape != (self.C, self.F, self.N, 2):
+        """``uvs``: (C,F,N,2) numpy array, or a float64 CUDA tensor of that shape (device copy)."""
+        on_device = hasattr(uvs, "is_cuda")
+        if not on_device:
+            uvs = np.ascontiguousarray(uvs, dtype=np.float64)
+        if tuple(uvs.shape) != (self.C, self.F, self.N, 2):
             raise ValueError("observation shape changed")
         if obj is not None:
             self._obj = np.ascontiguousarray(obj, dtype=np.float64)
-        check(self.lib.mcba_set_observations(self._h, uvs.ctypes.data_as(ctypes.c_void_p),
-                                             self._obj.ctypes.data_as(ctypes.c_void_p), 0))
+        if on_device:
+            if not uvs.is_cuda or uvs.dtype != self.torch.float64:
+                raise ValueError("device observations must be a float64 CUDA tensor")
+            uvs = uvs.contiguous()
+            self.stream.wait_stream(self.torch.cuda.current_stream(self.device))
+            d_obj = self._dev(self._obj)
+            check(self.lib.mcba_set_observations(self._h, _ptr(uvs), _ptr(d_obj), 1))
+        else:
+            check(self.lib.mcba_set_observations(self._h, uvs.ctypes.data_as(ctypes.c_void_p),
+                                                 self._obj.ctypes.data_as(ctypes.c_void_p), 0))
         check(self.lib.mcba_synchronize(self._h))   # uvs may be a temporary
 
     @property
