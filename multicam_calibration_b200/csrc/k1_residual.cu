@@ -149,33 +149,30 @@ __global__ void __launch_bounds__(256) tile_observations_kernel(const double2* _
   }
 }
 
-// finite scalars per (c,f) row (one warp per row) + number of observed corners
-__global__ void count_rows_kernel(const double* __restrict__ ref, long long rows, int N,
-                                  long long* __restrict__ counts, unsigned long long* __restrict__ n_obs) {
+// finite scalars per group of 32 consecutive (c,f,n) slots (one warp per group) + number of
+// observed corners: the exclusive scan of these counts positions every group of the compacted
+// residual vector (bundle_adjustment.py:97) without any per-row structure
+__global__ void count_groups_kernel(const double2* __restrict__ ref, long long slots, long long groups,
+                                    long long* __restrict__ counts, unsigned long long* __restrict__ n_obs) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = warp; row < rows; row += nwarps) {
-    const double* p = ref + row * 2 * N;
-    int cnt = 0, obs = 0;
-    for (int s0 = 0; s0 < 2 * N; s0 += 32) {   // uniform trip count: the shuffle needs all lanes
-      const int s = s0 + lane;
-      const double v = s < 2 * N ? p[s] : nan("");
-      const bool fin = v == v;
-      cnt += fin;
-      const double w = __shfl_xor_sync(0xffffffffu, v, 1);  // the other scalar of the corner
-      obs += ((s & 1) == 0) && (fin || (w == w));
+  unsigned long long obs = 0;
+  for (long long g = warp; g < groups; g += nwarps) {
+    const long long i = g * 32 + lane;
+    bool fu = false, fv = false;
+    if (i < slots) {
+      const double2 o = ref[i];
+      fu = o.x == o.x;
+      fv = o.y == o.y;
     }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-      obs += __shfl_xor_sync(0xffffffffu, obs, off);
-    }
+    const unsigned bu = __ballot_sync(0xffffffffu, fu), bv = __ballot_sync(0xffffffffu, fv);
     if (lane == 0) {
-      counts[row] = cnt;
-      if (obs) atomicAdd(n_obs, (unsigned long long)obs);
+      counts[g] = __popc(bu) + __popc(bv);
+      obs += __popc(bu | bv);
     }
   }
+  if (lane == 0 && obs) atomicAdd(n_obs, obs);
 }
 
 int launch_tile_observations(mcba_handle* h) {
@@ -215,30 +212,30 @@ int launch_tile_observations(mcba_handle* h) {
   return MCBA_OK;
 }
 
-// row offsets of the NaN compaction (bundle_adjustment.py:97); only K1 needs them
+// group offsets of the NaN compaction (bundle_adjustment.py:97); only K1 needs them
 int ensure_row_offsets(mcba_handle* h) {
   if (h->have_rows) return MCBA_OK;
   const Layout& L = h->L;
-  int grid;
-  const long long rows = (long long)L.C * L.F;
+  const long long slots = (long long)L.C * L.F * L.N, groups = (slots + 31) / 32;
   unsigned long long* d_nobs = nullptr;
   MCBA_CUDA(cudaMalloc(&d_nobs, sizeof(unsigned long long)));
   MCBA_CUDA(cudaMemsetAsync(d_nobs, 0, sizeof(unsigned long long), h->stream));
-  MCBA_CUDA(cudaMemsetAsync(h->d_row_off, 0, sizeof(long long) * (rows + 1), h->stream));
-  grid = (int)((rows * 32 + 255) / 256 < 148 * 16 ? (rows * 32 + 255) / 256 : 148 * 16);
+  MCBA_CUDA(cudaMemsetAsync(h->d_row_off, 0, sizeof(long long) * (groups + 1), h->stream));
+  int grid = (int)((groups * 32 + 255) / 256 < 148 * 16 ? (groups * 32 + 255) / 256 : 148 * 16);
   if (grid < 1) grid = 1;
-  count_rows_kernel<<<grid, 256, 0, h->stream>>>(h->d_obs_ref, rows, L.N, h->d_row_off, d_nobs);
+  count_groups_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref), slots, groups,
+                                                  h->d_row_off, d_nobs);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   size_t tmp_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_row_off, h->d_row_off, (int)(rows + 1), h->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_row_off, h->d_row_off, (int)(groups + 1), h->stream);
   void* d_tmp = nullptr;
   MCBA_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
-  MCBA_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, h->d_row_off, h->d_row_off, (int)(rows + 1), h->stream));
+  MCBA_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, h->d_row_off, h->d_row_off, (int)(groups + 1), h->stream));
   h->launches++;
   long long m = 0;
   unsigned long long nobs = 0;
-  MCBA_CUDA(cudaMemcpyAsync(&m, h->d_row_off + rows, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaMemcpyAsync(&m, h->d_row_off + groups, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   MCBA_CUDA(cudaMemcpyAsync(&nobs, d_nobs, sizeof(nobs), cudaMemcpyDeviceToHost, h->stream));
   MCBA_CUDA(cudaStreamSynchronize(h->stream));
   MCBA_CUDA(cudaFree(d_tmp));
@@ -250,58 +247,94 @@ int ensure_row_offsets(mcba_handle* h) {
 }
 
 // ---------------------------------------------------------------- residual vector / predictions
-// One warp per (c,f) row of 2N scalars.  The reference's operation order is kept
-// (world point first, then camera transform: bundle_adjustment.py:27-29,
-// geometry.py:304-305) so the result agrees with it to rounding.
-template <bool kCompact>
-__global__ void residuals_kernel(const double* __restrict__ x, const double* __restrict__ ref,
-                                 const double* __restrict__ obj, const CamConst* __restrict__ cams,
-                                 const long long* __restrict__ row_off, int C, long long F, int N,
-                                 double* __restrict__ out) {
+// K1, HBM bound (16 B read + up to 16 B written per (c,f,n) slot).  Two passes:
+//   row_transforms_kernel  one thread per (c,f) row: the composed transform X_c = Rcf X_o + tcf
+//                          (Rodrigues once per row instead of once per lane), 96 B per row;
+//   residuals_kernel       one warp per 32 consecutive (c,f,n) slots: one coalesced double2 load
+//                          and ONE projection per corner for both scalars, ballot-prefix
+//                          compaction in the reference's order (c,f,n,{u,v})
+//                          (bundle_adjustment.py:97) from per-group offsets.
+__global__ void row_transforms_kernel(const double* __restrict__ x, const CamConst* __restrict__ cams, int C,
+                                      long long F, double* __restrict__ rowT /* [C*F][12] */) {
+  const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (row >= (long long)C * F) return;
+  const int c = (int)(row / F);
+  const long long f = row % F;
+  const CamConst& cam = cams[c];
+  const double* ps = x + 12 * (long long)C + 6 * f;
+  const double rho[3] = {ps[0], ps[1], ps[2]}, tau[3] = {ps[3], ps[4], ps[5]};
+  double Rp[9], Rcf[9], tcf[3];
+  rodrigues(rho, Rp);
+  mat3_mul(cam.R, Rp, Rcf);
+  mat3_vec(cam.R, tau, tcf);
+  double2* o = reinterpret_cast<double2*>(rowT + row * 12);
+  o[0] = make_double2(Rcf[0], Rcf[1]);
+  o[1] = make_double2(Rcf[2], Rcf[3]);
+  o[2] = make_double2(Rcf[4], Rcf[5]);
+  o[3] = make_double2(Rcf[6], Rcf[7]);
+  o[4] = make_double2(Rcf[8], tcf[0] + cam.t[0]);
+  o[5] = make_double2(tcf[1] + cam.t[1], tcf[2] + cam.t[2]);
+}
+
+// Idx: unsigned int while C*F*N < 2^32 (two 32-bit divisions per lane instead of two 64-bit ones,
+// which alone made the kernel instruction bound: 180 -> ~70 warp instructions per group).
+template <bool kCompact, typename Idx>
+__global__ void __launch_bounds__(256) residuals_kernel(const double* __restrict__ rowT, const double2* __restrict__ ref,
+                                                        const double* __restrict__ obj,
+                                                        const CamConst* __restrict__ cams,
+                                                        const long long* __restrict__ grp_off, int C, long long F,
+                                                        int N, long long slots, double* __restrict__ out) {
+  extern __shared__ double s_obj[];
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_obj[i] = obj[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long rows = (long long)C * F;
-  for (long long row = warp; row < rows; row += nwarps) {
-    const int c = (int)(row / F);
-    const long long f = row % F;
-    const CamConst& cam = cams[c];
-    const double* ps = x + 12 * (long long)C + 6 * f;
-    const double rho[3] = {ps[0], ps[1], ps[2]};
-    double Rp[9];
-    rodrigues(rho, Rp);
-    long long base = kCompact ? row_off[row] : row * 2 * N;
-    for (int s0 = 0; s0 < 2 * N; s0 += 32) {
-      const int s = s0 + lane;
-      bool fin = false;
-      double val = 0.0;
-      if (s < 2 * N) {
-        const int n = s >> 1;
-        const double q[3] = {obj[3 * n], obj[3 * n + 1], obj[3 * n + 2]};
-        double Xw[3], Xc[3];
-        mat3_vec(Rp, q, Xw);
-        Xw[0] += ps[3]; Xw[1] += ps[4]; Xw[2] += ps[5];
-        mat3_vec(cam.R, Xw, Xc);
-        Xc[0] += cam.t[0]; Xc[1] += cam.t[1]; Xc[2] += cam.t[2];
-        const double xn = Xc[0] / Xc[2], yn = Xc[1] / Xc[2];
-        const double r2 = xn * xn + yn * yn;
-        const double d = 1.0 + cam.k1 * r2 + cam.k2 * (r2 * r2);
-        const double pred = (s & 1) ? (cam.fy * (Xc[1] * d) + cam.cy * Xc[2]) / Xc[2]
-                                    : (cam.fx * (Xc[0] * d) + cam.cx * Xc[2]) / Xc[2];
+  const long long groups = (slots + 31) / 32;
+  constexpr int kU = 4;   // groups per warp iteration: four independent 512-byte loads in flight per warp
+  for (long long g0 = warp * kU; g0 < groups; g0 += nwarps * kU) {
+    double2 o[kU];
+    long long off[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = (g0 + u) * 32 + lane;
+      o[u] = make_double2(0.0, 0.0);
+      off[u] = 0;
+      if (kCompact && i < slots) o[u] = ref[i];                       // coalesced: 512 contiguous bytes per warp
+      if (kCompact && g0 + u < groups) off[u] = grp_off[g0 + u];
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const long long i = (g0 + u) * 32 + lane;
+      bool fu = false, fv = false;
+      double ru = 0.0, rv = 0.0;
+      if (i < slots) {
+        const Idx row = (Idx)i / (Idx)N;
+        const int n = (int)((Idx)i - row * (Idx)N);
+        const int c = (int)(row / (Idx)F);
+        const CamConst& cam = cams[c];
+        const Intr in{cam.fx, cam.fy, cam.cx, cam.cy, cam.k1, cam.k2};
+        const double2* t2 = reinterpret_cast<const double2*>(rowT + (size_t)row * 12);   // <= 2-3 distinct rows per warp
+        const double2 t0 = t2[0], t1 = t2[1], t2v = t2[2], t3 = t2[3], t4 = t2[4], t5 = t2[5];
+        const double Rcf[9] = {t0.x, t0.y, t1.x, t1.y, t2v.x, t2v.y, t3.x, t3.y, t4.x};
+        const double tcf[3] = {t4.y, t5.x, t5.y};
+        double pu, pv;
+        project(in, Rcf, tcf, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], pu, pv);
         if (kCompact) {
-          const double o = ref[row * 2 * N + s];
-          fin = o == o;
-          val = o - pred;
+          fu = o[u].x == o[u].x;
+          fv = o[u].y == o[u].y;
+          ru = o[u].x - pu;
+          rv = o[u].y - pv;
         } else {
-          val = pred;
+          reinterpret_cast<double2*>(out)[i] = make_double2(pu, pv);
         }
       }
       if (kCompact) {
-        const unsigned mask = __ballot_sync(0xffffffffu, fin);
-        if (fin) out[base + __popc(mask & ((1u << lane) - 1))] = val;
-        base += __popc(mask);
-      } else if (s < 2 * N) {
-        out[base + s] = val;
+        const unsigned bu = __ballot_sync(0xffffffffu, fu), bv = __ballot_sync(0xffffffffu, fv);
+        const unsigned lt = (1u << lane) - 1u;
+        const long long pos = off[u] + __popc(bu & lt) + __popc(bv & lt);
+        if (fu) out[pos] = ru;
+        if (fv) out[pos + (fu ? 1 : 0)] = rv;
       }
     }
   }
@@ -314,12 +347,31 @@ static int rows_grid(long long rows) {
   return (int)g;
 }
 
-int launch_residuals(mcba_handle* h, const double* x, double* r_out) {
+static int launch_row_transforms(mcba_handle* h, const double* x) {
   const Layout& L = h->L;
   int rc = launch_prep_cameras(h, x);
   if (rc) return rc;
-  residuals_kernel<true><<<rows_grid((long long)L.C * L.F), 256, 0, h->stream>>>(
-      x, h->d_obs_ref, h->d_obj, h->d_cams, h->d_row_off, L.C, L.F, L.N, r_out);
+  const long long rows = (long long)L.C * L.F;
+  if (!h->d_rowT) MCBA_CUDA(cudaMalloc(&h->d_rowT, sizeof(double) * 12 * rows));   // K1 only: allocated on first use
+  row_transforms_kernel<<<(int)((rows + 255) / 256), 256, 0, h->stream>>>(x, h->d_cams, L.C, L.F, h->d_rowT);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+int launch_residuals(mcba_handle* h, const double* x, double* r_out) {
+  const Layout& L = h->L;
+  int rc = launch_row_transforms(h, x);
+  if (rc) return rc;
+  const long long slots = (long long)L.C * L.F * L.N;
+  if (slots < (1ll << 32))
+    residuals_kernel<true, unsigned int><<<rows_grid((slots + 31) / 32), 256, sizeof(double) * 3 * L.N, h->stream>>>(
+        h->d_rowT, reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obj, h->d_cams, h->d_row_off, L.C, L.F, L.N,
+        slots, r_out);
+  else
+    residuals_kernel<true, long long><<<rows_grid((slots + 31) / 32), 256, sizeof(double) * 3 * L.N, h->stream>>>(
+        h->d_rowT, reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obj, h->d_cams, h->d_row_off, L.C, L.F, L.N,
+        slots, r_out);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
@@ -327,10 +379,15 @@ int launch_residuals(mcba_handle* h, const double* x, double* r_out) {
 
 int launch_predict(mcba_handle* h, const double* x, double* uv_out) {
   const Layout& L = h->L;
-  int rc = launch_prep_cameras(h, x);
+  int rc = launch_row_transforms(h, x);
   if (rc) return rc;
-  residuals_kernel<false><<<rows_grid((long long)L.C * L.F), 256, 0, h->stream>>>(
-      x, nullptr, h->d_obj, h->d_cams, nullptr, L.C, L.F, L.N, uv_out);
+  const long long slots = (long long)L.C * L.F * L.N;
+  if (slots < (1ll << 32))
+    residuals_kernel<false, unsigned int><<<rows_grid((slots + 31) / 32), 256, sizeof(double) * 3 * L.N, h->stream>>>(
+        h->d_rowT, nullptr, h->d_obj, h->d_cams, nullptr, L.C, L.F, L.N, slots, uv_out);
+  else
+    residuals_kernel<false, long long><<<rows_grid((slots + 31) / 32), 256, sizeof(double) * 3 * L.N, h->stream>>>(
+        h->d_rowT, nullptr, h->d_obj, h->d_cams, nullptr, L.C, L.F, L.N, slots, uv_out);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

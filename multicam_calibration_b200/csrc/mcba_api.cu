@@ -177,7 +177,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_ALLOC(h->d_active, L.nTiles);
   MCBA_ALLOC(h->d_units, (size_t)C * L.nTiles);
   MCBA_ALLOC(h->d_unit_count, 128);
-  MCBA_ALLOC(h->d_row_off, (size_t)C * F + 1);
+  MCBA_ALLOC(h->d_row_off, ((size_t)C * F * N + 31) / 32 + 1);
   MCBA_ALLOC(h->d_x, n);
   MCBA_ALLOC(h->d_xtrial, n);
   MCBA_ALLOC(h->d_cams, C);
@@ -227,7 +227,7 @@ int mcba_destroy(mcba_handle* h) {
   if (h->solver) cusolverDnDestroy(h->solver);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
-                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count};
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {
     for (int i = 0; i < kProfEvents * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);

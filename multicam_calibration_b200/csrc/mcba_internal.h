@@ -54,7 +54,8 @@ struct mcba_handle {
   int* d_unit_count = nullptr;       // [0..C) live units per camera | [32..32+C] group prefix for K2p
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
-  long long* d_row_off = nullptr;  // (C*F + 1) exclusive scan of finite scalars per (c,f)
+  long long* d_row_off = nullptr;  // exclusive scan of finite scalars per group of 32 (c,f,n) slots
+  double* d_rowT = nullptr;        // [C*F][12] composed (camera o pose) transforms, K1 only (lazy)
   long long m = 0;                 // finite scalar residuals
   long long n_obs = 0;             // (c,f,n) with at least one finite scalar
   bool have_obs = false;
