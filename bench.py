@@ -167,7 +167,7 @@ def cpu_baseline(steps=1, warmup=0, frames=CPU_SAMPLE_FRAMES):
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
-        return
+        return None
     base = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_step"] * 1e3,
@@ -176,7 +176,7 @@ def run_reference(args):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 # ---------------------------------------------------------------------------------------------
@@ -344,9 +344,18 @@ def run_engine(args):
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_baseline(steps=2, warmup=0)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
+
+
+def _quiet_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr and return a
+    file object on the real stdout: the contract is ONE JSON line on stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -359,10 +368,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_engine(args)
+    out = _quiet_stdout()
+    line = run_reference(args) if args.impl == "reference" else run_engine(args)
+    if line is not None:
+        out.write(json.dumps(line) + "\n")
+        out.flush()
 
 
 if __name__ == "__main__":
