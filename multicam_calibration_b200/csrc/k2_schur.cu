@@ -50,7 +50,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 constexpr int kSyrkStages = 3;
-constexpr int kSyrkWarps = 8;     // consumer (DMMA) warps; warp kSyrkWarps is the copy producer
+// consumer (DMMA) warps kW = 8 (<= 96 tiles: 6 cameras) or 15 (up to 300 tiles: 16 cameras without
+// re-reading Z; 15 + 1 warps = 4 per scheduler leaves 128 registers per thread); warp kW is the copy producer
 constexpr int kZK = 6 * kTile;    // K extent of one tile of Z
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
@@ -66,6 +67,7 @@ struct SyrkParams {
 };
 
 // this warp's share of the nT tiles handled by CTA column blockIdx.y: [t0, t0 + cnt)
+template <int kSyrkWarps>
 __device__ __forceinline__ void syrk_tile_range(const SyrkParams& p, int warp, int& t0, int& cnt) {
   const int per_col = (p.nT + (int)gridDim.y - 1) / (int)gridDim.y;
   const int c0 = (int)blockIdx.y * per_col;
@@ -77,10 +79,14 @@ __device__ __forceinline__ void syrk_tile_range(const SyrkParams& p, int warp, i
   t0 = c0 + warp * base + (warp > first_big ? warp - first_big : 0);
 }
 
+constexpr int kSyrkSlots = 20;   // tiles per warp: 15 warps x 20 = the 300 tiles of 16 cameras
 template <int NT>
-__device__ __forceinline__ void syrk_stage(const double* __restrict__ st, const int (&offA)[12], const int (&offB)[12],
-                                           double (&acc)[12][2], int KW) {
-#pragma unroll 4
+__device__ __forceinline__ void syrk_stage(const double* __restrict__ st, const int (&offA)[kSyrkSlots],
+                                           const int (&offB)[kSyrkSlots], double (&acc)[kSyrkSlots][2], int KW) {
+  // K-steps in flight per warp: enough independent fragment loads to cover the shared-memory
+  // latency without spilling the accumulators
+  constexpr int kUnroll = NT <= 6 ? 4 : (NT <= 12 ? 2 : 1);
+#pragma unroll kUnroll
   for (int k0 = 0; k0 < KW; k0 += 4) {
 #pragma unroll
     for (int sl = 0; sl < NT; ++sl) {
@@ -91,6 +97,7 @@ __device__ __forceinline__ void syrk_stage(const double* __restrict__ st, const 
   }
 }
 
+template <int kSyrkWarps>
 __global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const SyrkParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ unsigned long long full_bar[kSyrkStages], empty_bar[kSyrkStages];
@@ -133,23 +140,23 @@ __global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const
 
   // ---------------- consumers: up to 12 tiles of the upper block triangle per warp ----------------
   int t0, cnt;
-  syrk_tile_range(p, warp, t0, cnt);
-  int offA[12], offB[12];
+  syrk_tile_range<kSyrkWarps>(p, warp, t0, cnt);
+  int offA[kSyrkSlots], offB[kSyrkSlots];
   {
     int I = 0, rem = t0;
     while (I < p.nb8 - 1 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
     int J = I + rem;
     if (J >= p.nb8) { I = 0; J = 0; }   // empty range
 #pragma unroll
-    for (int s = 0; s < 12; ++s) {
+    for (int s = 0; s < kSyrkSlots; ++s) {
       offA[s] = (I * 8 + (lane >> 2)) * ld + (lane & 3);
       offB[s] = (J * 8 + (lane >> 2)) * ld + (lane & 3);
       if (s + 1 < cnt) { ++J; if (J == p.nb8) { ++I; J = I; } }
     }
   }
-  double acc[12][2];
+  double acc[kSyrkSlots][2];
 #pragma unroll
-  for (int s = 0; s < 12; ++s) acc[s][0] = acc[s][1] = 0.0;
+  for (int s = 0; s < kSyrkSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
 
   for (int unit = 0; unit < n_units; ++unit) {
     const int s = unit % kSyrkStages;
@@ -168,6 +175,14 @@ __global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const
       case 10: syrk_stage<10>(st, offA, offB, acc, p.KW); break;
       case 11: syrk_stage<11>(st, offA, offB, acc, p.KW); break;
       case 12: syrk_stage<12>(st, offA, offB, acc, p.KW); break;
+      case 13: syrk_stage<13>(st, offA, offB, acc, p.KW); break;
+      case 14: syrk_stage<14>(st, offA, offB, acc, p.KW); break;
+      case 15: syrk_stage<15>(st, offA, offB, acc, p.KW); break;
+      case 16: syrk_stage<16>(st, offA, offB, acc, p.KW); break;
+      case 17: syrk_stage<17>(st, offA, offB, acc, p.KW); break;
+      case 18: syrk_stage<18>(st, offA, offB, acc, p.KW); break;
+      case 19: syrk_stage<19>(st, offA, offB, acc, p.KW); break;
+      case 20: syrk_stage<20>(st, offA, offB, acc, p.KW); break;
       default: break;
     }
     __syncwarp();
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const
     while (I < p.nb8 - 1 && rem >= p.nb8 - I) { rem -= p.nb8 - I; ++I; }
     int J = I + rem;
 #pragma unroll
-    for (int s = 0; s < 12; ++s) {
+    for (int s = 0; s < kSyrkSlots; ++s) {
       if (s < cnt) {
         *reinterpret_cast<double2*>(out + (size_t)(I * 8 + (lane >> 2)) * p.nc8 + J * 8 + 2 * (lane & 3)) =
             make_double2(acc[s][0], acc[s][1]);
@@ -193,18 +208,19 @@ __global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const
 }
 
 struct SyrkConfig {
-  int gy, KW;
+  int warps, gy, KW;
   size_t smem;
 };
 
 static SyrkConfig syrk_config(int nc) {
   SyrkConfig c;
   const int nc8 = (nc + 7) / 8 * 8, nb8 = nc8 / 8, nT = nb8 * (nb8 + 1) / 2;
-  c.gy = (nT + kSyrkWarps * 12 - 1) / (kSyrkWarps * 12);   // at most 12 tiles (24 accumulator doubles) per warp
+  c.warps = nT <= 8 * 12 ? 8 : 15;
+  c.gy = (nT + c.warps * kSyrkSlots - 1) / (c.warps * kSyrkSlots);   // at most kSyrkSlots tiles per warp
   static const int widths[] = {192, 96, 64, 48, 32, 16, 8};
   c.KW = 8;
   for (int w : widths) {
-    if ((size_t)kSyrkStages * nc8 * (w + 4) * sizeof(double) <= 200 * 1024) { c.KW = w; break; }
+    if ((size_t)kSyrkStages * nc8 * (w + 4) * sizeof(double) <= 220 * 1024) { c.KW = w; break; }
   }
   c.smem = (size_t)kSyrkStages * nc8 * (c.KW + 4) * sizeof(double);
   return c;
@@ -225,8 +241,13 @@ int launch_k2_syrk(mcba_handle* h) {
   p.nTiles = (int)L.nTiles;
   p.KW = c.KW;
   p.part = h->d_partSyrk;
-  MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-  k2_syrk_kernel<<<dim3(h->grid_syrk, c.gy), (kSyrkWarps + 1) * 32, c.smem, h->stream>>>(p);
+  if (c.warps == 8) {
+    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    k2_syrk_kernel<8><<<dim3(h->grid_syrk, c.gy), 9 * 32, c.smem, h->stream>>>(p);
+  } else {
+    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    k2_syrk_kernel<15><<<dim3(h->grid_syrk, c.gy), 16 * 32, c.smem, h->stream>>>(p);
+  }
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
