@@ -162,12 +162,19 @@ struct Proj {
   double x, y, iz, r2, d, A00, A01, A10, A11, su, sv, pu, pv;
 };
 
-__device__ __forceinline__ void project_shared(const IntrReg& cam, SrPtr sR, double qx, double qy, double qz, Proj& o) {
+// 1 / Z_c of a corner: issued ONE corner ahead of its use (it depends only on the pose, not on
+// the previous corner), which takes the MUFU + 5 dependent FMAs of the reciprocal off the
+// per-corner critical path at the price of one carried double.
+__device__ __forceinline__ double inverse_depth(SrPtr sR, double qx, double qy, double qz) {
+  return fast_rcp(fma(sR[6 * 32], qx, fma(sR[7 * 32], qy, fma(sR[8 * 32], qz, sR[11 * 32]))));
+}
+
+__device__ __forceinline__ void project_shared(const IntrReg& cam, SrPtr sR, double qx, double qy, double qz,
+                                               double iz, Proj& o) {
   // sR: this lane's [Rcf (9) | tcf (3)], stride 32 doubles between entries
   const double X = fma(sR[0 * 32], qx, fma(sR[1 * 32], qy, fma(sR[2 * 32], qz, sR[9 * 32])));
   const double Y = fma(sR[3 * 32], qx, fma(sR[4 * 32], qy, fma(sR[5 * 32], qz, sR[10 * 32])));
-  const double Z = fma(sR[6 * 32], qx, fma(sR[7 * 32], qy, fma(sR[8 * 32], qz, sR[11 * 32])));
-  o.iz = fast_rcp(Z);
+  o.iz = iz;
   o.x = X * o.iz;
   o.y = Y * o.iz;
   o.r2 = fma(o.x, o.x, o.y * o.y);
@@ -210,13 +217,17 @@ __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& 
   const int N = p.N;
   double2 o0 = ob[0];
   double2 o1 = N > 1 ? ob[kTile] : o0;
+  double iz_next = inverse_depth(sR, s_obj[0], s_obj[1], s_obj[2]);
 #pragma unroll 1
   for (int n = 0; n < N; ++n) {
     const double2 cur = o0;
     o0 = o1;
     if (n + 2 < N) o1 = ob[(size_t)(n + 2) * kTile];
+    const double iz = iz_next;
+    const int nn = n + 1 < N ? n + 1 : n;
+    iz_next = inverse_depth(sR, s_obj[3 * nn], s_obj[3 * nn + 1], s_obj[3 * nn + 2]);
     Proj pr;
-    project_shared(cam, sR, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], pr);
+    project_shared(cam, sR, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], iz, pr);
     {
       const bool hu = cur.x == cur.x;
       const double fu = hu ? cur.x - pr.pu : 0.0;
