@@ -20,6 +20,7 @@
 #ifndef MCBA_H_
 #define MCBA_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -190,6 +191,15 @@ int mcba_profile(mcba_handle* h, int enable, double* ms_out, int* n_out);
 /* FP64 vector-pipe peak of the device, measured with a dependency-free DFMA loop (fused
  * multiply-adds per second): the compute ceiling bench.py quotes beside the HBM roofline. */
 int mcba_measure_fp64_peak(int device, double* fma_per_s);
+
+/* Caller-owned PAGEABLE host buffers <-> device at PCIe rate: the numpy arrays that cross the
+ * reference's Python boundary (all_calib_uvs in, bundle_adjustment.py:195; the residual vector
+ * out, :97-98).  Host threads stage 4 MB chunks through pinned bounce buffers on their own copy
+ * streams, overlapping the host memcpy / first-touch page faults with the DMA; pinned buffers
+ * take one async copy.  Ordered after the work already queued on cuda_stream; the data is in
+ * place when the call returns. */
+int mcba_upload(int device, void* cuda_stream, void* d_dst, const void* h_src, size_t bytes);
+int mcba_download(int device, void* cuda_stream, void* h_dst, const void* d_src, size_t bytes);
 
 /* Number of kernels this handle has launched (bench.py gpu_launches). */
 int64_t mcba_kernel_launches(mcba_handle* h);

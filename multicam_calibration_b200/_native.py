@@ -77,6 +77,8 @@ _SIGNATURES = {
     "mcba_measure_fp64_peak": (_I, [_I, ctypes.POINTER(_D)]),
     "mcba_select_frames": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _D, _P, ctypes.POINTER(_D)]),
     "mcba_gather_frames": (_I, [_I, _P, _P, _I, _L, _I, _P, _L, _P]),
+    "mcba_upload": (_I, [_I, _P, _P, _P, ctypes.c_size_t]),
+    "mcba_download": (_I, [_I, _P, _P, _P, ctypes.c_size_t]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -127,3 +129,30 @@ def require_cuda():
         raise RuntimeError("multicam_calibration_b200 needs a CUDA device (B200, sm_100a); "
                            "there is no CPU fallback.")
     return torch
+
+
+def to_device(array, device=None):
+    """float64 numpy array -> CUDA tensor through ``mcba_upload`` (staged, PCIe rate for pageable
+    memory), ordered on torch's current stream of ``device``."""
+    import numpy as np
+    torch = require_cuda()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    a = np.ascontiguousarray(array, dtype=np.float64)
+    out = torch.empty(a.shape, dtype=torch.float64, device=f"cuda:{dev}")
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(load().mcba_upload(dev, stream, ctypes.c_void_p(out.data_ptr()), a.ctypes.data_as(ctypes.c_void_p),
+                             a.nbytes))
+    return out
+
+
+def to_host(tensor):
+    """CUDA tensor -> fresh numpy array through ``mcba_download`` (current stream of its device)."""
+    import numpy as np
+    torch = require_cuda()
+    t = tensor.contiguous()
+    dev = t.device.index
+    out = np.empty(tuple(t.shape), dtype=np.dtype(str(t.dtype).replace("torch.", "")))
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(load().mcba_download(dev, stream, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(t.data_ptr()),
+                               out.nbytes))
+    return out

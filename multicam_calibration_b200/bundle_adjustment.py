@@ -28,14 +28,14 @@ def embed_calib_objpoints(calib_objpoints, calib_poses):
     dev = torch.cuda.current_device()
     obj = np.ascontiguousarray(calib_objpoints, dtype=np.float64)
     poses = np.ascontiguousarray(calib_poses, dtype=np.float64)
-    d_obj = torch.as_tensor(obj).to(f"cuda:{dev}")
-    d_pose = torch.as_tensor(poses.reshape(-1, 6)).to(f"cuda:{dev}")
+    d_obj = _native.to_device(obj, dev)
+    d_pose = _native.to_device(poses.reshape(-1, 6), dev)
     F, N = d_pose.shape[0], obj.shape[0]
     d_out = torch.empty((F, N, 3), dtype=torch.float64, device=d_obj.device)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     check(lib.mcba_embed_points(dev, stream, ctypes.c_void_p(d_pose.data_ptr()), F,
                                 ctypes.c_void_p(d_obj.data_ptr()), N, ctypes.c_void_p(d_out.data_ptr())))
-    return d_out.cpu().numpy()
+    return _native.to_host(d_out)
 
 
 def predict_calib_uvs(all_extrinsics, all_intrinsics, calib_objpoints, calib_poses):
@@ -72,18 +72,29 @@ _problems = {}
 
 
 def _problem_for(all_calib_uvs, calib_objpoints):
-    """One cached device allocation per problem shape; observations are re-uploaded
-    on every call (the caller's array may have changed)."""
-    uvs = np.asarray(all_calib_uvs)
-    key = uvs.shape
+    """One cached device allocation (the workspaces of the last problem shape, ~0.7 GB at
+    BASELINE configs[2]); observations are re-uploaded on every call (the caller's array may
+    have changed).  ``all_calib_uvs``: numpy array or float64 CUDA tensor."""
+    torch = _native.require_cuda()
+    uvs = all_calib_uvs if hasattr(all_calib_uvs, "is_cuda") else np.asarray(all_calib_uvs)
+    key = (tuple(uvs.shape), torch.cuda.current_device())
     prob = _problems.get(key)
     if prob is None:
+        for old in _problems.values():
+            old.close()
         _problems.clear()
         prob = BAProblem(uvs, calib_objpoints)
         _problems[key] = prob
     else:
         prob.set_observations(uvs, calib_objpoints)
     return prob
+
+
+def release_device_memory():
+    """Free the cached device problem (workspaces kept between calls of the same shape)."""
+    for old in _problems.values():
+        old.close()
+    _problems.clear()
 
 
 def residuals(params, all_calib_uvs, calib_objpoints):
@@ -117,9 +128,9 @@ def _select_frames_device(all_calib_uvs, all_extrinsics, all_intrinsics, calib_o
     uvs = np.ascontiguousarray(all_calib_uvs, dtype=np.float64)
     C, F, N, _ = uvs.shape
     x_all = serialize_params(all_extrinsics, all_intrinsics, calib_poses)
-    d_uvs = torch.as_tensor(uvs).to(f"cuda:{dev}")
-    d_x = torch.as_tensor(np.ascontiguousarray(x_all, dtype=np.float64)).to(f"cuda:{dev}")
-    d_obj = torch.as_tensor(np.ascontiguousarray(calib_objpoints, dtype=np.float64)).to(f"cuda:{dev}")
+    d_uvs = _native.to_device(uvs, dev)
+    d_x = _native.to_device(x_all, dev)
+    d_obj = _native.to_device(calib_objpoints, dev)
     d_use = torch.empty(F, dtype=torch.uint8, device=f"cuda:{dev}")
     stats = (ctypes.c_double * 4)()
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -183,11 +194,16 @@ def bundle_adjust(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints
         del d_uvs
         x, result = distributed.solve_sharded(all_calib_uvs[:, use_frames], calib_objpoints, x0, **opt_kwargs)
     else:
-        prob = BAProblem(_gather_frames_device(d_uvs, use_frames), calib_objpoints)
+        prob = _problem_for(_gather_frames_device(d_uvs, use_frames), calib_objpoints)
         del d_uvs
-        try:
-            x, result = prob.solve(x0, **opt_kwargs)
-        finally:
-            prob.close()
+        x, result = prob.solve(x0, **opt_kwargs)
+        on_device = result["_lazy"].pop("fun")
+
+        def fun():   # result.fun on first access (bundle_adjustment.py:66-98 at the solution)
+            try:
+                return on_device()
+            except RuntimeError:   # the cached problem has moved on: rebuild from the caller's arrays
+                return residuals(x, all_calib_uvs[:, use_frames], calib_objpoints)
+        result.set_lazy("fun", fun)
     ext, intr, poses = deserialize_params(result.x, n_cameras)
     return ext, intr, poses, use_frames, result

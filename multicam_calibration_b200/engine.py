@@ -24,9 +24,46 @@ _UNSUPPORTED = ("jac", "jac_sparsity", "bounds", "tr_solver", "tr_options", "dif
 
 
 class OptimizeResult(dict):
-    """Attribute-access dict with the fields of ``scipy.optimize.OptimizeResult``."""
-    __getattr__ = dict.get
+    """Attribute-access dict with the fields of ``scipy.optimize.OptimizeResult``.
+
+    Fields registered with :meth:`set_lazy` (``fun``: the 2·O-entry residual vector at the
+    solution, 134 MB at BASELINE configs[2]) are computed on the device and brought to the
+    host on first access only; the solve itself never waits for them."""
     __setattr__ = dict.__setitem__
+
+    def set_lazy(self, name, thunk):
+        lazy = dict.get(self, "_lazy")
+        if lazy is None:
+            lazy = {}
+            dict.__setitem__(self, "_lazy", lazy)
+        lazy[name] = thunk
+        dict.pop(self, name, None)
+
+    def __missing__(self, name):
+        lazy = dict.get(self, "_lazy") or {}
+        if name in lazy:
+            value = lazy.pop(name)()
+            dict.__setitem__(self, name, value)
+            return value
+        raise KeyError(name)
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            return None
+
+    def get(self, name, default=None):
+        try:
+            return self[name]
+        except KeyError:
+            return default
+
+    def __contains__(self, name):
+        return dict.__contains__(self, name) or name in (dict.get(self, "_lazy") or {})
+
+    def keys(self):
+        return [k for k in dict.keys(self) if k != "_lazy"] + list(dict.get(self, "_lazy") or {})
 
     def __dir__(self):
         return list(self.keys())
@@ -133,8 +170,7 @@ class BAProblem:
             pass
 
     def _dev(self, a):
-        return self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(
-            f"cuda:{self.device}", non_blocking=False)
+        return _native.to_device(a, self.device)
 
     def _empty(self, *shape):
         return self.torch.empty(shape, dtype=self.torch.float64, device=f"cuda:{self.device}")
@@ -162,10 +198,11 @@ class BAProblem:
             self.stream.wait_stream(self.torch.cuda.current_stream(self.device))
             d_obj = self._dev(self._obj)
             check(self.lib.mcba_set_observations(self._h, _ptr(uvs), _ptr(d_obj), 1))
-        else:
-            check(self.lib.mcba_set_observations(self._h, uvs.ctypes.data_as(ctypes.c_void_p),
-                                                 self._obj.ctypes.data_as(ctypes.c_void_p), 0))
+        else:   # pageable numpy -> device at PCIe rate (mcba_upload), then the device path
+            d_uvs, d_obj = self._dev(uvs), self._dev(self._obj)
+            check(self.lib.mcba_set_observations(self._h, _ptr(d_uvs), _ptr(d_obj), 1))
         check(self.lib.mcba_synchronize(self._h))   # uvs may be a temporary
+        self._obs_token = object()
 
     @property
     def n_residuals(self):
@@ -190,14 +227,14 @@ class BAProblem:
         x = self._x(params)
         r = self._empty(self.n_residuals)
         check(self.lib.mcba_residuals(self._h, _ptr(x), _ptr(r)))
-        return r.cpu().numpy()
+        return _native.to_host(r)
 
     @_on_stream
     def predict(self, params):
         x = self._x(params)
         uv = self._empty(self.C, self.F, self.N, 2)
         check(self.lib.mcba_predict(self._h, _ptr(x), _ptr(uv)))
-        return uv.cpu().numpy()
+        return _native.to_host(uv)
 
     @_on_stream
     def jacobian_blocks(self, params):
@@ -206,7 +243,7 @@ class BAProblem:
         Jc = self._empty(self.C, self.F, self.N, 2, 12)
         Jp = self._empty(self.C, self.F, self.N, 2, 6)
         check(self.lib.mcba_jacobian_blocks(self._h, _ptr(x), _ptr(Jc), _ptr(Jp)))
-        return Jc.cpu().numpy(), Jp.cpu().numpy()
+        return _native.to_host(Jc), _native.to_host(Jp)
 
     @_on_stream
     def cost(self, params, loss="soft_l1", f_scale=1.0):
@@ -234,14 +271,26 @@ class BAProblem:
     def gradient(self):
         g = self._empty(self.n_params)
         check(self.lib.mcba_gradient(self._h, _ptr(g)))
-        return g.cpu().numpy()
+        return _native.to_host(g)
 
     @_on_stream
     def solve_step(self, lam):
         """Damped step from the system of the last :meth:`build_reduced`."""
         xn = self._empty(self.n_params)
         check(self.lib.mcba_solve_step(self._h, _ptr(self._x_last), float(lam), _ptr(xn)))
-        return xn.cpu().numpy()
+        return _native.to_host(xn)
+
+    def _fun_thunk(self, xs):
+        """Residual vector at ``xs`` on first access of ``result.fun``: from this problem when it
+        still holds the same observations, else from a device copy of them kept with the result."""
+        token = self._obs_token
+
+        def thunk():
+            if getattr(self, "_h", None) is not None and self._h.value and self._obs_token is token:
+                return self.residuals(xs)
+            raise RuntimeError("result.fun: the problem was closed or its observations replaced before the "
+                               "residual vector was requested; call residuals(result.x, uvs, objpoints)")
+        return thunk
 
     # ------------------------------------------------------------------ the solve
     @_on_stream
@@ -265,16 +314,16 @@ class BAProblem:
         grad = self._empty(self.n_params)
         res = Result()
         check(self.lib.mcba_lm_run(self._h, _ptr(x), ctypes.byref(opts), ctypes.byref(res), _ptr(grad)))
-        xs = x.cpu().numpy()
+        xs = _native.to_host(x)
         out = OptimizeResult(
-            x=xs, cost=res.cost, grad=grad.cpu().numpy(), optimality=res.optimality,
+            x=xs, cost=res.cost, grad=_native.to_host(grad), optimality=res.optimality,
             active_mask=np.zeros_like(xs), nfev=res.nfev, njev=res.njev, status=res.status,
             message=TERMINATION_MESSAGES.get(res.status, "unknown"), success=res.status > 0,
             jac=None, initial_cost=res.cost0, rms=res.rms, iterations=res.iterations,
             solve_ms=res.solve_ms, step_norm=res.step_norm, damping=res.lambda_,
             kernel_launches=res.kernel_launches, n_residuals=res.n_residuals)
         if self.world == 1:
-            out["fun"] = self.residuals(xs)
+            out.set_lazy("fun", self._fun_thunk(xs))
         if verbose >= 1:
             print(out.message)
             print(f"Function evaluations {res.nfev}, initial cost {res.cost0:.4e}, final cost "

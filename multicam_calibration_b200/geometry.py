@@ -122,7 +122,7 @@ def project_points(points, extrinsics, camera_matrix, dist_coefs=None):
     torch, lib, dev = _device_ctx()
     pts = np.ascontiguousarray(points, dtype=np.float64)
     lead = pts.shape[:-1]
-    d_pts = torch.as_tensor(pts.reshape(-1, 3)).to(f"cuda:{dev}")
+    d_pts = _native.to_device(pts.reshape(-1, 3), dev)
     d_uv = torch.empty((d_pts.shape[0], 2), dtype=torch.float64, device=d_pts.device)
     ext = np.ascontiguousarray(extrinsics, dtype=np.float64)
     K = np.ascontiguousarray(camera_matrix, dtype=np.float64)
@@ -131,7 +131,7 @@ def project_points(points, extrinsics, camera_matrix, dist_coefs=None):
     check(lib.mcba_project_points(dev, stream, ctypes.c_void_p(d_pts.data_ptr()), d_pts.shape[0],
                                   _h(ext), _h(K), None if dist is None else _h(dist),
                                   ctypes.c_void_p(d_uv.data_ptr())))
-    return d_uv.cpu().numpy().reshape(*lead, 2)
+    return _native.to_host(d_uv).reshape(*lead, 2)
 
 
 def undistort_points(uvs, camera_matrix, dist_coefs):
@@ -139,7 +139,7 @@ def undistort_points(uvs, camera_matrix, dist_coefs):
     torch, lib, dev = _device_ctx()
     uv = np.ascontiguousarray(uvs, dtype=np.float64)
     shape = uv.shape
-    d_in = torch.as_tensor(uv.reshape(-1, 2)).to(f"cuda:{dev}")
+    d_in = _native.to_device(uv.reshape(-1, 2), dev)
     d_out = torch.empty_like(d_in)
     dist = np.zeros(5)
     dc = np.asarray(dist_coefs, dtype=np.float64).ravel()[:5]
@@ -147,7 +147,7 @@ def undistort_points(uvs, camera_matrix, dist_coefs):
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     check(lib.mcba_undistort_points(dev, stream, ctypes.c_void_p(d_in.data_ptr()), d_in.shape[0],
                                     _h(camera_matrix), _h(dist), ctypes.c_void_p(d_out.data_ptr())))
-    return d_out.cpu().numpy().reshape(shape)
+    return _native.to_host(d_out).reshape(shape)
 
 
 def triangulate(all_uvs, all_extrinsics, all_intrinsics):
@@ -162,9 +162,9 @@ def triangulate(all_uvs, all_extrinsics, all_intrinsics):
     for c, (_, dc) in enumerate(all_intrinsics):
         dc = np.asarray(dc, dtype=np.float64).ravel()[:5]
         dists[c, :dc.size] = dc
-    d_uv = torch.as_tensor(uv).to(f"cuda:{dev}")
+    d_uv = _native.to_device(uv, dev)
     d_out = torch.empty((P, 3), dtype=torch.float64, device=d_uv.device)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     check(lib.mcba_triangulate(dev, stream, ctypes.c_void_p(d_uv.data_ptr()), C, P, _h(ext), _h(Ks),
                                _h(dists), ctypes.c_void_p(d_out.data_ptr())))
-    return d_out.cpu().numpy()
+    return _native.to_host(d_out)

@@ -346,3 +346,40 @@ def test_bundle_adjust_device_gather_equals_host_slicing():
     x, r = mcc.BAProblem(args[0][:, use], sc.objpoints).solve(x0, ftol=1e-10, xtol=1e-10, verbose=0)
     assert res.cost == pytest.approx(r.cost, rel=1e-12) and res.nfev == r.nfev
     assert np.allclose(res.x, x, rtol=0, atol=1e-9)
+
+
+# ------------------------------------------------------------------ host <-> device staging, lazy result fields
+@pytest.mark.parametrize("n", [0, 1, 1000, (8 << 20) // 8 - 3, 5 * (4 << 20) // 8 + 7, 29 * (4 << 20) // 8 + 12345])
+def test_staged_upload_download_round_trip(n):
+    """mcba_upload / mcba_download move pageable numpy buffers bit-exactly (sizes below the staging
+    threshold, an exact multiple of the chunk, ragged tails, more chunks than worker threads)."""
+    import torch
+    from multicam_calibration_b200 import _native
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal(n)
+    d = _native.to_device(a)
+    assert d.shape == (n,) and d.dtype == torch.float64
+    assert np.array_equal(d.cpu().numpy(), a)
+    d2 = d * 2.0 + 1.0                       # produced on the stream the download is ordered after
+    assert np.array_equal(_native.to_host(d2), a * 2.0 + 1.0)
+    pinned = torch.from_numpy(a.copy()).pin_memory()
+    assert np.array_equal(_native.to_device(pinned.numpy()).cpu().numpy(), a)
+
+
+def test_result_fun_is_lazy_and_matches_residuals():
+    g = load_golden("frontend")
+    ext, intr = split_cams(g["init_cams"])
+    np.random.seed(0)
+    e, i, p, use, result = mcc.bundle_adjust(g["uvs"], ext, intr, g["objpoints"], g["init_poses"],
+                                             n_frames=None, verbose=0)
+    assert not dict.__contains__(result, "fun") and "fun" in result and "fun" in result.keys()
+    r_ref = orc.residuals(result.x, g["uvs"][:, use], g["objpoints"])
+    fun = result.fun
+    assert dict.__contains__(result, "fun") and result["fun"] is fun
+    assert fun.shape == r_ref.shape and np.abs(fun - r_ref).max() <= 1e-10 * np.abs(r_ref).max()
+    # a result whose cached problem has been reused still produces fun (rebuilt from the caller's arrays)
+    np.random.seed(0)
+    *_, result2 = mcc.bundle_adjust(g["uvs"], ext, intr, g["objpoints"], g["init_poses"], n_frames=None, verbose=0)
+    mcc.residuals(result2.x, g["uvs"][:, use] + 1.0, g["objpoints"])
+    assert np.abs(result2.fun - r_ref).max() <= 1e-10 * np.abs(r_ref).max()
+    assert result2.missing_field is None
