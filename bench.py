@@ -34,6 +34,7 @@ CAMS, FRAMES, SIGMA, P_MISSING = 6, 50_000, 0.5, 0.2
 WORKLOAD = (f"{CAMS} cams x {FRAMES} frames/GPU x 35 corners, {int(P_MISSING * 100)}% missing detections, "
             f"sigma={SIGMA} px (BASELINE.json configs[2])")
 CPU_SAMPLE_FRAMES = 1000
+CPU_CONVERGE_FRAMES = 200    # scipy trf to convergence on this many frames: ~15 s of one host core
 ALG_FMA_PER_OBS = 250.0   # projection + Jacobian rows ~65, robust weights ~30, A_cf / q_cf accumulation ~150, bookkeeping ~5
 
 
@@ -145,7 +146,27 @@ def cpu_reference_step(sc_uvs, obj, x0, A):
     return f0, J
 
 
-def cpu_baseline(steps=1, warmup=0, frames=CPU_SAMPLE_FRAMES):
+def cpu_converge(frames):
+    """The reference path to convergence on a bounded sample of the workload: scipy least_squares
+    (trf + LSMR + 2-point FD through jac_sparsity, reference defaults ftol=1e-4, soft_l1) on the
+    oracle's restatement of bundle_adjust (bundle_adjustment.py:195-327)."""
+    import contextlib
+    import io
+    from multicam_calibration_b200.synthetic import make_scene
+    from oracle import np_oracle as orc
+    sc = make_scene(CAMS, frames, sigma=SIGMA, p_missing_view=P_MISSING, seed=0)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        *_, use, res = orc.bundle_adjust(*sc.init_args(), n_frames=None, verbose=0)
+    wall = time.perf_counter() - t0
+    rms = float(np.sqrt(np.mean(res.fun ** 2)))
+    return {"frames": frames, "frames_used": int(len(use)), "wall_s": wall, "nfev": int(res.nfev), "njev": int(res.njev),
+            "status": int(res.status), "rms_px": rms, "cost": float(res.cost),
+            "what": "scipy least_squares trf+LSMR, 2-point FD Jacobian through jac_sparsity, ftol=1e-4, single thread"}
+
+
+def cpu_baseline(steps=1, warmup=0, frames=CPU_SAMPLE_FRAMES, converge_frames=0):
     from multicam_calibration_b200.synthetic import make_scene
     from oracle import np_oracle as orc
     sc = make_scene(CAMS, frames, sigma=SIGMA, p_missing_view=P_MISSING, seed=0)
@@ -157,7 +178,8 @@ def cpu_baseline(steps=1, warmup=0, frames=CPU_SAMPLE_FRAMES):
     for _ in range(steps):
         cpu_reference_step(sc.uvs, sc.objpoints, x0, A)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": sc.n_obs / dt, "unit": UNIT, "cores": 1, "kind": "port",
+    conv = cpu_converge(converge_frames) if converge_frames else None
+    return {"converge": conv, "value": sc.n_obs / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": (f"{CAMS} cams x {frames} frames of the workload ({sc.n_obs} obs): numpy residuals + scipy "
                        f"2-point finite-difference Jacobian through jac_sparsity (18 colour groups), "
                        f"{dt:.2f} s/step, single thread (scipy path is serial); host has {os.cpu_count()} cores"),
@@ -168,12 +190,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
-    base = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1))
+    base = cpu_baseline(steps=args.steps, warmup=min(args.warmup, 1), converge_frames=CPU_CONVERGE_FRAMES)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": WORKLOAD, "sample_frames": CPU_SAMPLE_FRAMES},
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "converge")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     return line
@@ -281,6 +303,32 @@ def run_engine(args):
         ba_wall = time.perf_counter() - t0
         _, res_t = prob.solve(x0, ftol=1e-10, xtol=1e-10, verbose=0)
 
+    # ---- the public call a user of the reference makes: numpy arrays in, calibration out
+    api, api_same = None, None
+    if world == 1:
+        import contextlib
+        import io
+        import multicam_calibration_b200 as mcc
+        prob.close()
+
+        def api_call(scene):
+            out = []
+            for _ in range(3):    # first call allocates the cached device problem
+                np.random.seed(0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    *_, use, r = mcc.bundle_adjust(*scene.init_args(), n_frames=None, verbose=0)
+                out.append((time.perf_counter() - t0, r, len(use)))
+            dt, r, n_use = min(out, key=lambda t: t[0])
+            return {"wall_ms": dt * 1e3, "first_call_ms": out[0][0] * 1e3, "device_ms": r.solve_ms, "iterations": r.iterations,
+                    "nfev": r.nfev, "status": r.status, "rms_px": r.rms, "cost": r.cost, "frames_used": n_use}
+        api = api_call(sc)
+        api["call"] = ("multicam_calibration_b200.bundle_adjust(uvs, extrinsics, intrinsics, objpoints, poses, n_frames=None): "
+                       "pageable numpy in, frame selection + upload + LM solve, calibration out")
+        if not args.no_cpu_baseline:
+            api_same = api_call(make_scene(args.cams, CPU_CONVERGE_FRAMES, sigma=SIGMA, p_missing_view=P_MISSING, seed=0))
+
     # max over ranks, totals over ranks
     if world > 1:
         t = torch.tensor([ms, e2e_ms, res.solve_ms], dtype=torch.float64, device="cuda")
@@ -339,13 +387,16 @@ def run_engine(args):
                     "call": "mcba_build_reduced_host (pinned host uvs, x -> S, b)"},
             "gpu_launches": launches_total,
             "ba_converge": {"device_ms": ba_ms, "wall_s": ba_wall, "iterations": res.iterations, "nfev": res.nfev,
-                            "status": res.status, "rms_px": res.rms, "cost": res.cost, "tol": "ftol=1e-4 (reference default)",
+                            "status": res.status, "rms_px": res.rms, "cost": res.cost, "tol": "ftol=1e-4 (reference default)", "api": api,
                             "tight": {"device_ms": res_t.solve_ms, "iterations": res_t.iterations, "rms_px": res_t.rms,
                                       "cost": res_t.cost, "optimality": res_t.optimality, "tol": "ftol=xtol=1e-10"}},
         }
         if world == 1 and not args.no_cpu_baseline:
-            base = cpu_baseline(steps=2, warmup=0)
+            base = cpu_baseline(steps=2, warmup=0, converge_frames=CPU_CONVERGE_FRAMES)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            conv = base["converge"]
+            conv["engine_same_sample"] = api_same
+            line["cpu_baseline"]["converge"] = conv
     if world > 1:
         dist.destroy_process_group()
     return line if rank == 0 else None

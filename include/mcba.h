@@ -164,6 +164,25 @@ int mcba_gather_frames(int device, void* cuda_stream, const double* d_uvs, int n
                        int64_t n_frames, int n_points, const int64_t* d_idx, int64_t n_used,
                        double* d_out);
 
+/* ---- initialisation algebra (the step before bundle_adjust; calibration.py) ----
+ * calibration.py:116-143 estimate_pairwise_camera_transform: d_poses1, d_poses2 (F,6) board poses
+ * seen by two cameras (NaN rows = not detected); h_transform[6] = per-component median over the
+ * common frames of vec(T2_f T1_f^-1) (geometry.py:178-197 vector form); *h_n_common = number of
+ * common frames (may be NULL).  No common frame -> NaN, like np.median of an empty array. */
+int mcba_pairwise_transform(int device, void* cuda_stream, const double* d_poses1,
+                            const double* d_poses2, int64_t n_frames, double* h_transform,
+                            int64_t* h_n_common);
+/* calibration.py:245-277 consensus_calib_poses: d_all_poses (C,F,6), h_extrinsics (C,6) world ->
+ * camera; d_poses (F,6) = nanmedian over cameras of vec(T_world->cam^-1 T_board->cam), NaN rows
+ * where no camera detected the board. */
+int mcba_consensus_poses(int device, void* cuda_stream, const double* d_all_poses,
+                         const double* h_extrinsics, int n_cameras, int64_t n_frames,
+                         double* d_poses);
+/* geometry.py:38-65 rodrigues_inv (dim = 3: d_matrices (P,3,3) -> d_vectors (P,3)) and
+ * geometry.py:178-197 get_transformation_vector (dim = 4: (P,4,4) -> (P,6)). */
+int mcba_transformation_vectors(int device, void* cuda_stream, const double* d_matrices,
+                                int64_t n, int dim, double* d_vectors);
+
 /* geometry.py:277-325 project_points for P points and one camera:
  * d_points (P,3), ext (6), K (3x3 row major, skew honoured), dist (k1,k2) or NULL. */
 int mcba_project_points(int device, void* cuda_stream, const double* d_points, int64_t n_points,

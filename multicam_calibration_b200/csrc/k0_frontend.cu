@@ -162,6 +162,21 @@ __global__ void gather_frames_kernel(const double2* __restrict__ src, int C, lon
   }
 }
 
+// The device's default stream-ordered memory pool keeps freed blocks (release threshold raised
+// once per device), so the work arrays of the one-shot entry points cost no cudaMalloc / cudaFree
+// after their first call.
+int keep_async_pool(int device) {
+  static bool pool_ready[64] = {};
+  if (device >= 0 && device < 64 && !pool_ready[device]) {
+    cudaMemPool_t pool;
+    MCBA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    MCBA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pool_ready[device] = true;
+  }
+  return MCBA_OK;
+}
+
 }  // namespace mcba
 
 using namespace mcba;
@@ -179,14 +194,7 @@ extern "C" int mcba_select_frames(int device, void* cuda_stream, const double* d
   // One stream-ordered allocation carved into the work arrays.  The device's default memory pool
   // keeps the block between calls (release threshold raised once), so a repeated call pays no
   // cudaMalloc / cudaFree (those cost ~15 ms here for ~0.3 ms of kernels and a 2 ms sort).
-  static bool pool_ready[64] = {};
-  if (device >= 0 && device < 64 && !pool_ready[device]) {
-    cudaMemPool_t pool;
-    MCBA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long keep = ~0ull;
-    MCBA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    pool_ready[device] = true;
-  }
+  { int rc = keep_async_pool(device); if (rc) return rc; }
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const double*)nullptr, (double*)nullptr, (int)total, 0, 64, st);
   auto up = [](size_t b) { return (b + 255) / 256 * 256; };

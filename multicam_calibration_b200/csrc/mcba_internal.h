@@ -112,6 +112,8 @@ void set_error(const std::string& msg);
     }                                                                                     \
   } while (0)
 
+int keep_async_pool(int device);   // k0_frontend.cu
+
 // kernel launchers (defined in the .cu files)
 int launch_prep_cameras(mcba_handle* h, const double* x);
 int launch_tile_observations(mcba_handle* h);
