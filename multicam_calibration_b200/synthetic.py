@@ -159,3 +159,38 @@ def make_keypoints(n_points=1_000_000, n_cameras=6, sigma=0.3, p_missing=0.2, se
         uv[rng.random(n_points) < p_missing] = np.nan
         all_uvs.append(uv)
     return all_uvs, ext, intr, pts
+
+
+def make_camera_poses(n_cameras=6, n_frames=500, p_missing=0.25, sigma_rot=0.01, sigma_trans=1.0, seed=0):
+    """Per-camera board poses as ``estimate_pose`` (cv2.solvePnP per camera and frame,
+    calibration.py:72-113) would return them: ``T_board->cam = T_world->cam T_board->world`` of a
+    :func:`make_scene` rig, perturbed by a small rigid noise, NaN rows where the camera did not
+    see the complete board.  Returns ``(all_calib_poses (C,F,6), true extrinsics (C,6), true
+    board poses (F,6))`` with camera 0 as the world frame (what estimate_all_extrinsics recovers)."""
+    rng = np.random.default_rng([seed, 7])
+    cams = make_scene(n_cameras, 1, sigma=0.0, seed=seed).true_cams
+    board_world = np.concatenate([rng.normal(0, 0.6, (n_frames, 3)), rng.normal(0, 60, (n_frames, 3))], axis=1)
+
+    def mat(v):
+        T = np.zeros(v.shape[:-1] + (4, 4))
+        T[..., :3, :3] = _rotmat(v[..., :3])
+        T[..., :3, 3] = v[..., 3:]
+        T[..., 3, 3] = 1.0
+        return T
+
+    def vec(T):
+        R = T[..., :3, :3]
+        w = np.stack([R[..., 2, 1] - R[..., 1, 2], R[..., 0, 2] - R[..., 2, 0], R[..., 1, 0] - R[..., 0, 1]], axis=-1)
+        th = np.arccos(np.clip((np.trace(R, axis1=-2, axis2=-1) - 1) / 2, -1, 1))[..., None]
+        n = np.linalg.norm(w, axis=-1, keepdims=True)
+        return np.concatenate([w * th / np.where(n > 0, n, 1.0), T[..., :3, 3]], axis=-1)
+    T_wc = mat(cams[:, 6:12])                         # world -> camera
+    T_bw = mat(board_world)                           # board -> world
+    T_root = np.linalg.inv(T_wc[0])                   # camera 0 becomes the world frame
+    ext = vec(T_wc @ T_root)
+    board = vec(np.linalg.inv(T_root) @ T_bw)
+    noise = np.concatenate([rng.normal(0, sigma_rot, (n_cameras, n_frames, 3)),
+                            rng.normal(0, sigma_trans, (n_cameras, n_frames, 3))], axis=-1)
+    poses = vec(mat(noise) @ (T_wc[:, None] @ T_bw[None]))
+    poses[rng.random((n_cameras, n_frames)) < p_missing] = np.nan
+    return poses, ext, board

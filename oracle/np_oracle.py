@@ -472,6 +472,60 @@ def analytic_jac_for_scipy(params, all_calib_uvs, calib_objpoints):
 
 
 # --------------------------------------------------------------------------
+# initialisation algebra (calibration.py)
+# --------------------------------------------------------------------------
+def estimate_pairwise_camera_transform(camera1_poses, camera2_poses):
+    """calibration.py:116-143 -- median over the frames both cameras detected of
+    ``vec(T2 inv(T1))`` (4x4 matrices, LAPACK inverse, like the reference)."""
+    p1, p2 = np.asarray(camera1_poses, dtype=float), np.asarray(camera2_poses, dtype=float)
+    both = ~(np.isnan(p1).any(1) | np.isnan(p2).any(1))
+    rel = transformation_matrix(p2[both]) @ np.linalg.inv(transformation_matrix(p1[both]))
+    return np.median(transformation_vector(rel), axis=0)
+
+
+def camera_spanning_tree(all_calib_poses, root=0):
+    """calibration.py:146-197 -- networkx maximum spanning tree over the co-detection counts
+    (networkx is the reference's own, unpinned, dependency for this step), edges oriented away
+    from the root and ordered by hop distance."""
+    import networkx as nx
+    poses = np.asarray(all_calib_poses, dtype=float)
+    seen = ~np.isnan(poses).any(2)
+    n = len(poses)
+    graph = nx.Graph()
+    graph.add_nodes_from(range(n))
+    graph.add_weighted_edges_from((i, j, (seen[i] & seen[j]).sum()) for i in range(n) for j in range(i + 1, n))
+    tree = nx.maximum_spanning_tree(graph)
+    hops = nx.shortest_path_length(tree, source=root)
+    oriented = [tuple(sorted(e, key=hops.get)) for e in tree.edges]
+    return sorted(oriented, key=lambda e: hops[e[0]])
+
+
+def estimate_all_extrinsics(all_calib_poses, root=0):
+    """calibration.py:200-242 -- chain the pairwise transforms along the spanning tree."""
+    poses = np.asarray(all_calib_poses, dtype=float)
+    T = [None] * len(poses)
+    T[root] = np.eye(4)
+    tree = camera_spanning_tree(poses, root=root)
+    for c1, c2 in tree:
+        T[c2] = transformation_matrix(estimate_pairwise_camera_transform(poses[c1], poses[c2])) @ T[c1]
+    return np.array([transformation_vector(t) for t in T]), tree
+
+
+def consensus_calib_poses(all_calib_poses, all_extrinsics):
+    """calibration.py:245-277 -- board poses of every detecting camera mapped to world
+    coordinates (``inv(T_world->cam) T_board->cam``), nanmedian over cameras."""
+    import warnings
+    poses = np.asarray(all_calib_poses, dtype=float)
+    world = np.full_like(poses, np.nan)
+    for c, (p, ext) in enumerate(zip(poses, np.asarray(all_extrinsics, dtype=float))):
+        ok = ~np.isnan(p).any(-1)
+        world[c, ok] = transformation_vector(np.linalg.inv(transformation_matrix(ext)) @ transformation_matrix(p[ok]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        return np.nanmedian(world, axis=0)
+
+
+# --------------------------------------------------------------------------
 # gauge-invariant comparison helpers (SURVEY.md H1)
 # --------------------------------------------------------------------------
 def relative_camera_transforms(all_extrinsics):

@@ -383,3 +383,58 @@ def test_result_fun_is_lazy_and_matches_residuals():
     mcc.residuals(result2.x, g["uvs"][:, use] + 1.0, g["objpoints"])
     assert np.abs(result2.fun - r_ref).max() <= 1e-10 * np.abs(r_ref).max()
     assert result2.missing_field is None
+
+
+# ------------------------------------------------------------------ initialisation algebra
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_initialisation_algebra_matches_reference_fixture(tag):
+    g = load_golden("init")
+    poses = g[f"{tag}_poses"]
+    pair = mcc.estimate_pairwise_camera_transform(poses[0], poses[1])
+    np.testing.assert_allclose(pair, g[f"{tag}_pair01"], rtol=0, atol=1e-9)
+    for root, key in ((0, ""), (2, "_root2")):
+        ext, tree = mcc.estimate_all_extrinsics(poses, root=root)
+        assert tree == [tuple(int(v) for v in e) for e in g[f"{tag}_tree{key}"]]
+        np.testing.assert_allclose(ext, g[f"{tag}_ext{key}"], rtol=0, atol=1e-9)
+    cons = mcc.consensus_calib_poses(poses, g[f"{tag}_ext"])
+    assert np.array_equal(np.isnan(cons), np.isnan(g[f"{tag}_consensus"]))
+    np.testing.assert_allclose(cons, g[f"{tag}_consensus"], rtol=0, atol=1e-9)
+
+
+def test_initialisation_algebra_large_against_oracle_and_truth():
+    from multicam_calibration_b200.synthetic import make_camera_poses
+    poses, ext_true, board_true = make_camera_poses(7, 20000, p_missing=0.3, seed=5)
+    poses[:, 11] = np.nan
+    ext, tree = mcc.estimate_all_extrinsics(poses, root=0)
+    ext_o, tree_o = orc.estimate_all_extrinsics(poses, root=0)
+    assert tree == [tuple(int(v) for v in e) for e in tree_o]
+    np.testing.assert_allclose(ext, ext_o, rtol=0, atol=1e-9)
+    cons = mcc.consensus_calib_poses(poses, ext)
+    cons_o = orc.consensus_calib_poses(poses, ext)
+    assert np.array_equal(np.isnan(cons), np.isnan(cons_o)) and np.isnan(cons[11]).all()
+    np.testing.assert_allclose(cons, cons_o, rtol=0, atol=1e-9)
+    dT = orc.transformation_matrix(ext) - orc.transformation_matrix(ext_true)
+    assert np.abs(dT[:, :3, :3]).max() < 0.01 and np.abs(dT[:, :3, 3]).max() < 5.0
+    # no common frame: NaN like np.median of an empty selection; wrong shapes raise
+    a, b = poses[0].copy(), poses[1].copy()
+    a[::2], b[1::2] = np.nan, np.nan
+    assert np.isnan(mcc.estimate_pairwise_camera_transform(a, b)).all()
+    with pytest.raises(ValueError):
+        mcc.estimate_pairwise_camera_transform(poses[0], poses[1][:-1])
+    with pytest.raises(ValueError):
+        mcc.consensus_calib_poses(poses, ext[:-1])
+
+
+def test_device_transformation_vectors_match_reference():
+    import ctypes
+    import torch
+    from multicam_calibration_b200 import _native
+    g = load_golden("init")
+    lib = _native.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for key, dim, width in (("R", 3, 3), ("T", 4, 6)):
+        d_in = _native.to_device(g[key])
+        d_out = torch.empty((len(g[key]), width), dtype=torch.float64, device="cuda")
+        _native.check(lib.mcba_transformation_vectors(torch.cuda.current_device(), stream, ctypes.c_void_p(d_in.data_ptr()),
+                                                      len(g[key]), dim, ctypes.c_void_p(d_out.data_ptr())))
+        np.testing.assert_allclose(_native.to_host(d_out), g[f"{key}_vec"], rtol=0, atol=1e-12)

@@ -101,3 +101,51 @@ def test_convergence_fixture_is_a_stationary_point():
     assert cost == pytest.approx(float(g["cost_tight"]), rel=1e-12)
     assert float(g["cost_tight"]) <= float(g["cost_default"])
     assert orc.reprojection_rms(g["x_tight"], uv, g["objpoints"]) == pytest.approx(float(g["rms_tight"]), rel=1e-12)
+
+
+# ------------------------------------------------------------------ initialisation algebra (calibration.py)
+def _tree(a):
+    return [tuple(int(v) for v in e) for e in a]
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_initialisation_algebra_matches_reference(tag):
+    g = load_golden("init")
+    poses = g[f"{tag}_poses"]
+    np.testing.assert_allclose(orc.estimate_pairwise_camera_transform(poses[0], poses[1]), g[f"{tag}_pair01"],
+                               rtol=0, atol=1e-12)
+    ext, tree = orc.estimate_all_extrinsics(poses, root=0)
+    assert _tree(tree) == _tree(g[f"{tag}_tree"])
+    np.testing.assert_allclose(ext, g[f"{tag}_ext"], rtol=0, atol=1e-10)
+    ext2, tree2 = orc.estimate_all_extrinsics(poses, root=2)
+    assert _tree(tree2) == _tree(g[f"{tag}_tree_root2"])
+    np.testing.assert_allclose(ext2, g[f"{tag}_ext_root2"], rtol=0, atol=1e-10)
+    cons = orc.consensus_calib_poses(poses, g[f"{tag}_ext"])
+    assert np.array_equal(np.isnan(cons), np.isnan(g[f"{tag}_consensus"]))
+    assert np.isnan(cons[5]).all()                                     # a frame no camera saw
+    assert np.isnan(cons[6]).any() == np.isnan(poses[0, 6]).any()      # a frame only camera 0 can have seen
+    np.testing.assert_allclose(cons, g[f"{tag}_consensus"], rtol=0, atol=1e-10)
+
+
+def test_host_spanning_tree_orders_edges_like_the_reference():
+    """The package's networkx-free spanning tree against the reference fixtures and, under heavy
+    ties, against the oracle's networkx version (what the reference calls)."""
+    from multicam_calibration_b200.calibration import get_camera_spanning_tree
+    g = load_golden("init")
+    for tag in ("a", "b"):
+        assert get_camera_spanning_tree(g[f"{tag}_poses"], root=0) == _tree(g[f"{tag}_tree"])
+        assert get_camera_spanning_tree(g[f"{tag}_poses"], root=2) == _tree(g[f"{tag}_tree_root2"])
+    pytest.importorskip("networkx")
+    rng = np.random.default_rng(1)
+    for _ in range(60):
+        C, F = int(rng.integers(2, 9)), int(rng.integers(1, 6))
+        poses = rng.normal(size=(C, F, 6))
+        poses[rng.random((C, F)) < 0.5] = np.nan
+        root = int(rng.integers(0, C))
+        assert get_camera_spanning_tree(poses, root=root) == _tree(orc.camera_spanning_tree(poses, root=root))
+
+
+def test_transformation_vectors_match_reference():
+    g = load_golden("init")
+    np.testing.assert_allclose(orc.rodrigues_inv(g["R"]), g["R_vec"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(orc.transformation_vector(g["T"]), g["T_vec"], rtol=0, atol=1e-15)
