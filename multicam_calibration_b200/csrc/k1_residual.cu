@@ -183,7 +183,8 @@ int launch_tile_observations(mcba_handle* h) {
   iota_kernel<<<blocks, 256, 0, h->stream>>>(h->d_perm, L.Fpad);
   h->launches += 2;
   static const bool no_sort = getenv("MCBA_NO_FRAME_SORT") != nullptr;
-  if (L.C <= 12 && !no_sort) {   // 2^C patterns: beyond that tiles would not share a mask anyway
+  if (!no_sort) {   // the 32 frames of a tile share the leading ~log2(nTiles) bits of the sorted key: all cameras
+                    // when 2^C <= nTiles, the highest-numbered ones otherwise
     size_t bytes = 0;
     unsigned int* keys_out = h->d_mask + L.Fpad;
     int* vals_out = h->d_perm + L.Fpad;
@@ -207,6 +208,8 @@ int launch_tile_observations(mcba_handle* h) {
   group_prefix_kernel<<<1, 32, 0, h->stream>>>(h->d_unit_count, L.C, h->prod_warps, h->d_unit_count + 32);
   // dead units are never written by K2p: their hand-off stays zero
   MCBA_CUDA(cudaMemsetAsync(h->d_H, 0, sizeof(double) * (size_t)L.nTiles * L.C * 63 * kTile, h->stream));
+  // ... and K2c never writes their Z rows
+  MCBA_CUDA(cudaMemsetAsync(h->d_Z, 0, sizeof(double) * (size_t)L.Fpad * 6 * L.nc, h->stream));
   h->launches += 4;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

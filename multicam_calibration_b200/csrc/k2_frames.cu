@@ -25,6 +25,7 @@ struct K2CParams {
   long long F, nTiles;
   const double* H;       // [tile][c][63][32]
   const int* perm;       // tile slot -> frame index in x (-1 = padding)
+  const unsigned int* active;   // [tile] bit c: camera c has observations in the tile
   const double* x;       // 12C + 6F
   const CamConst* cams;
   double lambda;
@@ -247,14 +248,31 @@ __global__ void __launch_bounds__(kC * 32, 2) k2c_ring_kernel(const K2CParams p)
   constexpr int nc = 12 * kC;
   const int c = warp;
   const int n_it = p.nTiles > blockIdx.x ? (int)((p.nTiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  auto issue = [&](int it) {   // thread 0 only
+  // thread 0 only: one bulk copy per LIVE camera of the tile (frames are sorted by visibility
+  // mask, so a dead (tile, camera) unit has an all-zero hand-off that is never read, and its Z rows,
+  // zeroed once when the observations were tiled, are never written)
+  auto issue = [&](int it) {
     const long long tile = blockIdx.x + (long long)it * gridDim.x;
-    const unsigned bytes = kStage * sizeof(double);
+    const unsigned m = p.active[tile] & ((1u << kC) - 1u);
+    constexpr unsigned kUnitBytes = kHandoff * kTile * sizeof(double);
+    const unsigned bytes = (unsigned)__popc(m) * kUnitBytes;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2c_smem_u32(&full_bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     k2c_smem_u32(stage)),
-                 "l"(p.H + (size_t)tile * kStage), "r"(bytes), "r"(k2c_smem_u32(&full_bar))
-                 : "memory");
+    if (m == (1u << kC) - 1u) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       k2c_smem_u32(stage)),
+                   "l"(p.H + (size_t)tile * kStage), "r"(bytes), "r"(k2c_smem_u32(&full_bar))
+                   : "memory");
+    } else {
+#pragma unroll
+      for (int cc = 0; cc < kC; ++cc) {
+        if ((m >> cc) & 1u)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           k2c_smem_u32(stage + (size_t)cc * kHandoff * kTile)),
+                       "l"(p.H + (size_t)tile * kStage + (size_t)cc * kHandoff * kTile), "r"(kUnitBytes),
+                       "r"(k2c_smem_u32(&full_bar))
+                       : "memory");
+      }
+    }
   };
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(&full_bar)));
@@ -272,6 +290,7 @@ __global__ void __launch_bounds__(kC * 32, 2) k2c_ring_kernel(const K2CParams p)
     const long long tile = blockIdx.x + (long long)it * gridDim.x;
     const long long f = p.perm[tile * kTile + lane];
     const bool fvalid = f >= 0;
+    const bool live = (p.active[tile] >> c) & 1u;   // warp-uniform
     double pose[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(kC * 32, 2) k2c_ring_kernel(const K2CParams p)
       for (int i = 0; i < 21; ++i) Vp[i] = 0.0;
 #pragma unroll
       for (int i = 0; i < 6; ++i) gq[i] = 0.0;
-      pose_block_add(h, Rc, K, Vp, gq);
+      if (live) pose_block_add(h, Rc, K, Vp, gq);
       // round 1: V''[0..10] through s_X, g'' through this camera's (consumed) q_ext slots
 #pragma unroll
       for (int i = 0; i < kXchg; ++i) s_X[(c * kXchg + i) * kTile + lane] = Vp[i];
@@ -323,7 +342,7 @@ __global__ void __launch_bounds__(kC * 32, 2) k2c_ring_kernel(const K2CParams p)
     double Linv[21], yv[6], gp[6];
     pose_block_factor(Vpp, gpp, Jl, p.lambda, p.D2pose + (size_t)tile * 6 * 32 + lane, warp == 0, Linv, yv, gp, gmax);
     if (warp == 0) store_pose_outputs(p, tile, f, fvalid, lane, Linv, yv, gp);
-    z_rows(h, Rc, K, Jl, Linv, yv, p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane, zy);
+    if (live) z_rows(h, Rc, K, Jl, Linv, yv, p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane, zy);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our generic writes (g'') precede the next bulk copy
     __syncthreads();   // every warp is done with the stage and with s_X
     if (threadIdx.x == 0 && it + 1 < n_it) issue(it + 1);
@@ -408,6 +427,7 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
   p.nTiles = L.nTiles;
   p.H = h->d_H;
   p.perm = h->d_perm;
+  p.active = h->d_active;
   p.x = x;
   p.cams = h->d_cams;
   p.lambda = lambda;
