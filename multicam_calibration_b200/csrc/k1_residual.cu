@@ -208,6 +208,7 @@ int launch_tile_observations(mcba_handle* h) {
   group_prefix_kernel<<<1, 32, 0, h->stream>>>(h->d_unit_count, L.C, h->prod_warps, h->d_unit_count + 32);
   // dead units are never written by K2p: their hand-off stays zero
   MCBA_CUDA(cudaMemsetAsync(h->d_H, 0, sizeof(double) * (size_t)L.nTiles * L.C * 63 * kTile, h->stream));
+  h->alt_stale = true;
   // ... and K2c never writes their Z rows
   MCBA_CUDA(cudaMemsetAsync(h->d_Z, 0, sizeof(double) * (size_t)L.Fpad * 6 * L.nc, h->stream));
   h->launches += 4;

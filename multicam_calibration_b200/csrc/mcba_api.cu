@@ -87,6 +87,58 @@ static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, do
   return MCBA_OK;
 }
 
+// K2c + SYRK + finalize (+ all-reduce) on the K2p outputs the handle currently points at
+static int evaluate_tail(mcba_handle* h, const double* x, double lambda) {
+  int rc;
+  if ((rc = launch_k2_consumer(h, x, lambda))) return rc;
+  if ((rc = launch_k2_syrk(h))) return rc;
+  if ((rc = launch_finalize(h))) return rc;
+  return allreduce_packed(h, h->d_red, h->L.redLen);
+}
+
+// out[0..2] = fixed-order sum over K2p's per-CTA partials {0.5 sum rho, sum f^2, count}
+__global__ void sum_scalars_kernel(const double* __restrict__ partS, int n, double* __restrict__ out) {
+  __shared__ double s[3][32];
+  const int lane = threadIdx.x;
+  double a = 0, b = 0, k = 0;
+  for (int i = lane; i < n; i += 32) {
+    a += partS[(size_t)i * kRsNum + kRsCost];
+    b += partS[(size_t)i * kRsNum + kRsSumSq];
+    k += partS[(size_t)i * kRsNum + kRsCount];
+  }
+  s[0][lane] = a; s[1][lane] = b; s[2][lane] = k;
+  __syncwarp();
+  if (lane < 3) {
+    double t = 0;
+    for (int i = 0; i < 32; ++i) t += s[lane][i];
+    out[lane] = t;
+  }
+}
+
+static void swap_k2p_outputs(mcba_handle* h) {
+  std::swap(h->d_H, h->d_H_alt);
+  std::swap(h->d_partU, h->d_partU_alt);
+  std::swap(h->d_partS, h->d_partS_alt);
+  std::swap(h->d_cams, h->d_cams_alt);
+}
+
+static int ensure_alt_outputs(mcba_handle* h) {
+  const Layout& L = h->L;
+  const size_t h_bytes = sizeof(double) * (size_t)L.nTiles * L.C * 63 * kTile;
+  if (!h->d_H_alt) {
+    MCBA_CUDA(cudaMalloc((void**)&h->d_H_alt, h_bytes));
+    MCBA_CUDA(cudaMalloc((void**)&h->d_partU_alt, sizeof(double) * (size_t)h->grid_frames * L.C * kAcc));
+    MCBA_CUDA(cudaMalloc((void**)&h->d_partS_alt, sizeof(double) * (size_t)h->grid_frames * kRsNum));
+    MCBA_CUDA(cudaMalloc((void**)&h->d_cams_alt, sizeof(CamConst) * L.C));
+    h->alt_stale = true;
+  }
+  if (h->alt_stale) {
+    MCBA_CUDA(cudaMemsetAsync(h->d_H_alt, 0, h_bytes, h->stream));
+    h->alt_stale = false;
+  }
+  return MCBA_OK;
+}
+
 static int read_eval(mcba_handle* h, EvalOut* out) {
   const Layout& L = h->L;
   const long long tail = L.redLen - L.offB;
@@ -227,7 +279,7 @@ int mcba_destroy(mcba_handle* h) {
   if (h->solver) cusolverDnDestroy(h->solver);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
-                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT};
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {
     for (int i = 0; i < kProfEvents * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);
@@ -396,6 +448,7 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
   MCBA_CUDA(cudaMemsetAsync(h->d_D2pose, 0, sizeof(double) * L.nTiles * 6 * kTile, h->stream));
   MCBA_CUDA(cudaMemsetAsync(h->d_D2cam, 0, sizeof(double) * L.nc, h->stream));
 
+  if ((rc = ensure_alt_outputs(h))) return rc;
   double lambda = opt.lambda0, nu = 2.0;
   EvalOut ev;
   // Gauss-Newton weights: IRLS far from the minimum, scipy's Triggs scaling once the cost
@@ -422,7 +475,15 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
     if (nfev >= max_nfev) { status = 0; break; }
     if ((rc = solve_reduced(h, lambda))) return rc;
     if ((rc = launch_backsub(h, x, xt, lambda))) return rc;
-    if ((rc = launch_cost(h, xt, opt.loss, opt.f_scale, h->d_scal))) return rc;
+    // The trial point is evaluated with the full per-observation kernel K2p into the second set of
+    // outputs: its partial sums give the trial cost, and when the step is accepted (the common
+    // case) its hand-off is what K2c needs next -- no separate cost pass, no second walk.
+    swap_k2p_outputs(h);
+    const int trial_loss = loss_code();
+    if ((rc = launch_prep_cameras(h, xt))) return rc;
+    if ((rc = launch_k2_producer(h, xt, trial_loss, opt.f_scale))) return rc;
+    sum_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_partS, h->grid_frames, h->d_scal);
+    h->launches++;
     if ((rc = allreduce_packed(h, h->d_scal, 12))) return rc;
     MCBA_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_scal, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
     MCBA_CUDA(cudaMemcpyAsync(h->h_pinned + 16, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
@@ -451,7 +512,11 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       nu = 2.0;
       ++iter;
       if (irls && opt.hessian == MCBA_HESSIAN_AUTO && actual < 1e-2 * cost) irls = false;
-      if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;
+      if (loss_code() != trial_loss) {   // the Gauss-Newton weights change here (once per solve): walk again
+        if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;
+      } else {
+        if ((rc = evaluate_tail(h, x, lambda))) return rc;
+      }
       if ((rc = read_eval(h, &ev))) return rc;
       ++njev;
       const double cost_prev = cost;
@@ -460,11 +525,12 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       if (term != -2) status = term;
       else if (ev.gnorm < opt.gtol) status = 1;
     } else {
+      swap_k2p_outputs(h);   // back to the outputs of the current point
       if (term == 3 || term == 4) { status = 3; break; }   // step too small to matter (xtol)
       lambda *= nu;
       nu *= 2.0;
       if (lambda > opt.lambda_max) { status = -1; set_error("damping exceeded lambda_max without finding a descent step"); break; }
-      if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale, true))) return rc;   // pose damping is baked into Z: K2c + SYRK only
+      if ((rc = evaluate_tail(h, x, lambda))) return rc;   // pose damping is baked into Z: K2c + SYRK only
       if ((rc = read_eval(h, &ev))) return rc;
     }
   }

@@ -65,6 +65,13 @@ struct mcba_handle {
   double* d_xtrial = nullptr;
   mcba::CamConst* d_cams = nullptr;
   double* d_H = nullptr;      // K2p -> K2c hand-off [tile][c][63][32]
+  // second set of K2p outputs (allocated by the first mcba_lm_run): the LM loop evaluates K2p at
+  // the TRIAL point into these and swaps the two sets when the step is accepted
+  double* d_H_alt = nullptr;
+  double* d_partU_alt = nullptr;
+  double* d_partS_alt = nullptr;
+  mcba::CamConst* d_cams_alt = nullptr;
+  bool alt_stale = true;      // d_H_alt needs zeroing (dead units are never written)
   double* d_partG = nullptr;  // [n_part_c] max |pose gradient| per K2c partial
   double* d_partZy = nullptr; // [n_part_c][12C] partial sums of Z_f y_f
   double* d_Z = nullptr;
