@@ -216,19 +216,65 @@ int launch_tile_observations(mcba_handle* h) {
   return MCBA_OK;
 }
 
-// group offsets of the NaN compaction (bundle_adjustment.py:97); only K1 needs them
+// ---- chunked K1 path --------------------------------------------------------------------------
+// A chunk = one camera's 32 consecutive frames = ONE contiguous block of 32*N double2 in the
+// reference layout (C,F,N,2), for the observations as well as for the predictions.
+constexpr int kChunkFrames = 32;
+
+static bool k1_use_chunks() {
+  static const bool flat = getenv("MCBA_K1_FLAT") != nullptr;
+  return !flat;
+}
+
+// finite scalars of every chunk (one warp per chunk, coalesced) + number of observed corners
+__global__ void count_chunks_kernel(const double2* __restrict__ ref, int C, long long F, int N, long long nBlk,
+                                    long long* __restrict__ counts, unsigned long long* __restrict__ n_obs) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long obs = 0;
+  for (long long u = warp; u < (long long)C * nBlk; u += nwarps) {
+    const int c = (int)(u / nBlk);
+    const long long f0 = (u % nBlk) * kChunkFrames;
+    const long long nf = F - f0 < kChunkFrames ? F - f0 : kChunkFrames;
+    const double2* p = ref + ((long long)c * F + f0) * N;
+    int cnt = 0;
+    for (long long i = lane; i < nf * N; i += 32) {
+      const double2 o = p[i];
+      const bool fu = o.x == o.x, fv = o.y == o.y;
+      cnt += (fu ? 1 : 0) + (fv ? 1 : 0);
+      obs += (fu | fv) ? 1 : 0;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0) counts[u] = cnt;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) obs += __shfl_xor_sync(0xffffffffu, obs, off);
+  if (lane == 0 && obs) atomicAdd(n_obs, obs);
+}
+
+// offsets of the NaN compaction (bundle_adjustment.py:97) per chunk (or per group of 32 slots on
+// the fallback path for very large boards); only K1 needs them
 int ensure_row_offsets(mcba_handle* h) {
   if (h->have_rows) return MCBA_OK;
   const Layout& L = h->L;
-  const long long slots = (long long)L.C * L.F * L.N, groups = (slots + 31) / 32;
+  const bool chunks = k1_use_chunks();
+  const long long slots = (long long)L.C * L.F * L.N;
+  const long long nBlk = (L.F + kChunkFrames - 1) / kChunkFrames;
+  const long long groups = chunks ? (long long)L.C * nBlk : (slots + 31) / 32;
   unsigned long long* d_nobs = nullptr;
   MCBA_CUDA(cudaMalloc(&d_nobs, sizeof(unsigned long long)));
   MCBA_CUDA(cudaMemsetAsync(d_nobs, 0, sizeof(unsigned long long), h->stream));
   MCBA_CUDA(cudaMemsetAsync(h->d_row_off, 0, sizeof(long long) * (groups + 1), h->stream));
   int grid = (int)((groups * 32 + 255) / 256 < 148 * 16 ? (groups * 32 + 255) / 256 : 148 * 16);
   if (grid < 1) grid = 1;
-  count_groups_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref), slots, groups,
-                                                  h->d_row_off, d_nobs);
+  if (chunks)
+    count_chunks_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref), L.C, L.F, L.N, nBlk,
+                                                    h->d_row_off, d_nobs);
+  else
+    count_groups_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref), slots, groups,
+                                                    h->d_row_off, d_nobs);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   size_t tmp_bytes = 0;
@@ -250,8 +296,148 @@ int ensure_row_offsets(mcba_handle* h) {
   return MCBA_OK;
 }
 
-// ---------------------------------------------------------------- residual vector / predictions
-// K1, HBM bound (16 B read + up to 16 B written per (c,f,n) slot).  Two passes:
+// K1 (chunked): 16 B read + up to 16 B written per (c,f,n) slot, no auxiliary pass.
+// Each warp owns chunks (camera c, frames f0..f0+31).
+//   phase A  lane = frame: the composed transform X_c = R_c R(rho_f) X_o + (R_c tau_f + t_c) of
+//            the chunk's 32 (camera, frame) rows goes to the warp's 3 KB of shared memory
+//            (Rodrigues once per row, not once per slot);
+//   phase B  lane = slot: the chunk's nf * N slots are walked in their memory order, four groups
+//            of 32 in flight per warp: one coalesced 16-byte load per slot, the row's transform
+//            from shared memory (at most two distinct rows per group: broadcast reads), one
+//            projection for both scalars, then either the ballot-compacted residuals in the
+//            reference's order c, f, n, {u, v} (bundle_adjustment.py:97) from a running offset
+//            that starts at the chunk's scanned offset, or the coalesced predictions.
+// Per group of 32 slots this is ~80 warp instructions (45 of them FP64) against ~160 for the
+// per-slot indexing of the fallback kernel below.
+#ifndef MCBA_K1_CTAS
+#define MCBA_K1_CTAS 4
+#endif
+template <bool kCompact>
+__global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(const double* __restrict__ x, const double2* __restrict__ ref,
+                                                              const double* __restrict__ obj,
+                                                              const long long* __restrict__ chunk_off, int C, long long F,
+                                                              int N, long long nBlk, double* __restrict__ out) {
+  extern __shared__ __align__(16) double k1_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+  double* s_T = k1_smem + (size_t)warp * kChunkFrames * 12;          // [32 rows][12]
+  double* s_cam = k1_smem + (size_t)nWarps * kChunkFrames * 12;       // [C][18]: fx fy cx cy k1 k2 | R (9) | t (3)
+  double* s_obj = s_cam + (size_t)C * 18;                             // [3 N]
+  for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_obj[i] = obj[i];
+  if (threadIdx.x < C) {   // camera constants in the kernel itself: no separate launch in front of it
+    const double* p = x + 12 * threadIdx.x;
+    double* sc = s_cam + 18 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sc[i] = p[i];
+    const double r[3] = {p[6], p[7], p[8]};
+    double R[9];
+    rodrigues(r, R);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) sc[6 + i] = R[i];
+    sc[15] = p[9]; sc[16] = p[10]; sc[17] = p[11];
+  }
+  __syncthreads();
+  const long long nUnits = (long long)C * nBlk;
+  const long long gw = (long long)blockIdx.x * nWarps + warp, stride = (long long)gridDim.x * nWarps;
+  // slot -> row within the chunk: i / N for i < 32 N <= 2^16 N ... exact for i * N < 2^32 with a 32-bit reciprocal
+  const unsigned inv_n = (unsigned)((0x100000000ull + (unsigned)N - 1) / (unsigned)N);
+  const unsigned lt = (1u << lane) - 1u;
+  for (long long u = gw; u < nUnits; u += stride) {
+    const int c = (int)(u / nBlk);
+    const long long f0 = (u % nBlk) * kChunkFrames;
+    const int nf = (int)(F - f0 < kChunkFrames ? F - f0 : kChunkFrames);
+    const double* sc = s_cam + 18 * c;
+    const Intr in{sc[0], sc[1], sc[2], sc[3], sc[4], sc[5]};
+    __syncwarp();   // the previous chunk's readers are done with s_T
+    if (lane < nf) {
+      const double* ps = x + 12 * (long long)C + 6 * (f0 + lane);
+      const double rho[3] = {ps[0], ps[1], ps[2]}, tau[3] = {ps[3], ps[4], ps[5]};
+      double Rc[9], Rp[9], Rcf[9], tcf[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Rc[i] = sc[6 + i];
+      rodrigues(rho, Rp);
+      mat3_mul(Rc, Rp, Rcf);
+      mat3_vec(Rc, tau, tcf);
+      double2* t = reinterpret_cast<double2*>(s_T + lane * 12);
+      t[0] = make_double2(Rcf[0], Rcf[1]);
+      t[1] = make_double2(Rcf[2], Rcf[3]);
+      t[2] = make_double2(Rcf[4], Rcf[5]);
+      t[3] = make_double2(Rcf[6], Rcf[7]);
+      t[4] = make_double2(Rcf[8], tcf[0] + sc[15]);
+      t[5] = make_double2(tcf[1] + sc[16], tcf[2] + sc[17]);
+    }
+    __syncwarp();
+    const int total = nf * N;
+    const long long base = ((long long)c * F + f0) * N;     // first slot of the chunk
+    long long off = kCompact ? chunk_off[u] : 0;
+    constexpr int kU = 4;
+    for (int i0 = 0; i0 < total; i0 += 32 * kU) {
+      double2 o[kU];
+#pragma unroll
+      for (int g = 0; g < kU; ++g) {
+        const int i = i0 + g * 32 + lane;
+        o[g] = make_double2(0.0, 0.0);
+        if (kCompact && i < total) o[g] = ref[base + i];
+      }
+#pragma unroll
+      for (int g = 0; g < kU; ++g) {
+        const int i = i0 + g * 32 + lane;
+        if (i0 + g * 32 >= total) break;   // warp-uniform
+        bool fu = false, fv = false;
+        double ru = 0.0, rv = 0.0;
+        if (i < total) {
+          const int row = (int)__umulhi((unsigned)i, inv_n);
+          const int n = i - row * N;
+          const double2* t = reinterpret_cast<const double2*>(s_T + row * 12);
+          const double2 t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4], t5 = t[5];
+          const double Rcf[9] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y, t4.x};
+          const double tcf[3] = {t4.y, t5.x, t5.y};
+          double pu, pv;
+          project(in, Rcf, tcf, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], pu, pv);
+          if (kCompact) {
+            fu = o[g].x == o[g].x;
+            fv = o[g].y == o[g].y;
+            ru = o[g].x - pu;
+            rv = o[g].y - pv;
+          } else {
+            reinterpret_cast<double2*>(out)[base + i] = make_double2(pu, pv);
+          }
+        }
+        if (kCompact) {
+          const unsigned bu = __ballot_sync(0xffffffffu, fu), bv = __ballot_sync(0xffffffffu, fv);
+          const long long pos = off + __popc(bu & lt) + __popc(bv & lt);
+          if (fu) out[pos] = ru;
+          if (fv) out[pos + (fu ? 1 : 0)] = rv;
+          off += __popc(bu) + __popc(bv);
+        }
+      }
+    }
+  }
+}
+
+static int launch_chunks(mcba_handle* h, const double* x, double* out, bool compact) {
+  const Layout& L = h->L;
+  const int warps = 8;
+  const long long nBlk = (L.F + kChunkFrames - 1) / kChunkFrames;
+  const long long units = (long long)L.C * nBlk;
+  const size_t smem = sizeof(double) * ((size_t)warps * kChunkFrames * 12 + 18 * (size_t)L.C + 3 * (size_t)L.N);
+  long long grid = (units + warps - 1) / warps;
+  if (grid > 8LL * h->n_sm) grid = 8LL * h->n_sm;
+  if (smem > 48 * 1024) {
+    MCBA_CUDA(cudaFuncSetAttribute(residual_chunks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MCBA_CUDA(cudaFuncSetAttribute(residual_chunks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  if (compact)
+    residual_chunks_kernel<true><<<(int)grid, warps * 32, smem, h->stream>>>(
+        x, reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obj, h->d_row_off, L.C, L.F, L.N, nBlk, out);
+  else
+    residual_chunks_kernel<false><<<(int)grid, warps * 32, smem, h->stream>>>(x, nullptr, h->d_obj, nullptr, L.C, L.F, L.N, nBlk,
+                                                                             out);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+// K1 without the chunk structure (kept for comparison; MCBA_K1_FLAT=1 selects it).  Two passes:
 //   row_transforms_kernel  one thread per (c,f) row: the composed transform X_c = Rcf X_o + tcf
 //                          (Rodrigues once per row instead of once per lane), 96 B per row;
 //   residuals_kernel       one warp per 32 consecutive (c,f,n) slots: one coalesced double2 load
@@ -365,6 +551,7 @@ static int launch_row_transforms(mcba_handle* h, const double* x) {
 
 int launch_residuals(mcba_handle* h, const double* x, double* r_out) {
   const Layout& L = h->L;
+  if (k1_use_chunks()) return launch_chunks(h, x, r_out, true);
   int rc = launch_row_transforms(h, x);
   if (rc) return rc;
   const long long slots = (long long)L.C * L.F * L.N;
@@ -383,6 +570,7 @@ int launch_residuals(mcba_handle* h, const double* x, double* r_out) {
 
 int launch_predict(mcba_handle* h, const double* x, double* uv_out) {
   const Layout& L = h->L;
+  if (k1_use_chunks()) return launch_chunks(h, x, uv_out, false);
   int rc = launch_row_transforms(h, x);
   if (rc) return rc;
   const long long slots = (long long)L.C * L.F * L.N;

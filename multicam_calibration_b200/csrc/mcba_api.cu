@@ -229,7 +229,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_ALLOC(h->d_active, L.nTiles);
   MCBA_ALLOC(h->d_units, (size_t)C * L.nTiles);
   MCBA_ALLOC(h->d_unit_count, 128);
-  MCBA_ALLOC(h->d_row_off, ((size_t)C * F * N + 31) / 32 + 1);
+  MCBA_ALLOC(h->d_row_off, std::max(((size_t)C * F * N + 31) / 32, (size_t)C * ((F + 31) / 32)) + 1);
   MCBA_ALLOC(h->d_x, n);
   MCBA_ALLOC(h->d_xtrial, n);
   MCBA_ALLOC(h->d_cams, C);
