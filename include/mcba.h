@@ -188,6 +188,12 @@ int mcba_transformation_vectors(int device, void* cuda_stream, const double* d_m
 int mcba_project_points(int device, void* cuda_stream, const double* d_points, int64_t n_points,
                         const double* h_ext, const double* h_K, const double* h_dist,
                         double* d_uv);
+/* The same projection into all C cameras of a rig in one pass over the points (what
+ * bundle_adjustment.py:56-62 predict_calib_uvs and a reprojection-error evaluation loop over):
+ * h_ext (C,6), h_K (C,3,3), h_dist (C,2) or NULL; d_uv (C,P,2). */
+int mcba_project_points_multi(int device, void* cuda_stream, const double* d_points,
+                              int64_t n_points, int n_cameras, const double* h_ext,
+                              const double* h_K, const double* h_dist, double* d_uv);
 /* bundle_adjustment.py:10-30 embed_calib_objpoints: d_poses (F,6), d_obj (N,3) -> d_world (F,N,3). */
 int mcba_embed_points(int device, void* cuda_stream, const double* d_poses, int64_t n_frames,
                       const double* d_obj, int n_points, double* d_world);

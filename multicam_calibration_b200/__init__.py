@@ -9,7 +9,7 @@ produces bundle_adjust's initial guess (calibration.py:116-277).
 from .geometry import (rodrigues, rodrigues_inv, rigid_transform_from_correspondences,
                        apply_rigid_transform, get_transformation_matrix, get_transformation_vector,
                        get_projection_matrix, euclidean_to_homogenous, homogeneous_to_euclidean,
-                       project_points, undistort_points, triangulate)
+                       project_points, project_points_multi, undistort_points, triangulate)
 from .bundle_adjustment import (embed_calib_objpoints, predict_calib_uvs, residuals,
                                 bundle_adjustment_sparsity, serialize_params, deserialize_params,
                                 bundle_adjust, select_frames)

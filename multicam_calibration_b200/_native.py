@@ -69,6 +69,7 @@ _SIGNATURES = {
     "mcba_comm_unique_id": (_I, [_P]),
     "mcba_comm_init": (_I, [_P, _P, _I, _I]),
     "mcba_project_points": (_I, [_I, _P, _P, _L, _P, _P, _P, _P]),
+    "mcba_project_points_multi": (_I, [_I, _P, _P, _L, _I, _P, _P, _P, _P]),
     "mcba_embed_points": (_I, [_I, _P, _P, _L, _P, _I, _P]),
     "mcba_undistort_points": (_I, [_I, _P, _P, _L, _P, _P, _P]),
     "mcba_triangulate": (_I, [_I, _P, _P, _I, _L, _P, _P, _P, _P]),

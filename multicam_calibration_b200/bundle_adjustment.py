@@ -16,12 +16,12 @@ import numpy as np
 from . import _native
 from ._native import check
 from .engine import BAProblem
-from .geometry import project_points
+from .geometry import project_points, project_points_multi
 
 na = np.newaxis
 
 
-def embed_calib_objpoints(calib_objpoints, calib_poses):
+def embed_calib_objpoints(calib_objpoints, calib_poses, _keep_on_device=False):
     """(N,3), (F,6) -> (F,N,3) world points (bundle_adjustment.py:10-30)."""
     torch = _native.require_cuda()
     lib = _native.load()
@@ -35,14 +35,17 @@ def embed_calib_objpoints(calib_objpoints, calib_poses):
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     check(lib.mcba_embed_points(dev, stream, ctypes.c_void_p(d_pose.data_ptr()), F,
                                 ctypes.c_void_p(d_obj.data_ptr()), N, ctypes.c_void_p(d_out.data_ptr())))
-    return _native.to_host(d_out)
+    if _keep_on_device:
+        return d_out
+    return _native.to_host(d_out).reshape(*poses.shape[:-1], N, 3)
 
 
 def predict_calib_uvs(all_extrinsics, all_intrinsics, calib_objpoints, calib_poses):
-    """(C,F,N,2) predicted corner positions (bundle_adjustment.py:33-63)."""
-    world = embed_calib_objpoints(calib_objpoints, calib_poses)
-    return np.stack([project_points(world, ext, *intr)
-                     for ext, intr in zip(all_extrinsics, all_intrinsics)])
+    """(C,F,N,2) predicted corner positions (bundle_adjustment.py:33-63): the world points stay
+    on the device and are projected into every camera in one pass."""
+    d_world = embed_calib_objpoints(calib_objpoints, calib_poses, _keep_on_device=True)
+    F, N = d_world.shape[0], d_world.shape[1]
+    return project_points_multi(None, all_extrinsics, all_intrinsics, _device_points=(d_world.reshape(-1, 3), (F, N)))
 
 
 def serialize_params(all_extrinsics, all_intrinsics, calib_poses):

@@ -32,6 +32,53 @@ __global__ void project_points_kernel(const double* __restrict__ pts, long long 
   }
 }
 
+// All cameras of a rig in one pass: each point is read once (24 B) and projected into the C
+// views (16 B written per view); uv is (C,P,2).  Points are staged through shared memory so that
+// the stride-3 reads become coalesced 8-byte rows.
+constexpr int kProjByValue = 16;   // cameras passed in the kernel's parameter space (3 KB of the 4 KB limit)
+struct ProjCamPack {
+  ProjCam c[kProjByValue];
+};
+
+__global__ void __launch_bounds__(256) project_points_multi_kernel(const double* __restrict__ pts, long long P, int C,
+                                                                   const __grid_constant__ ProjCamPack pack,
+                                                                   const ProjCam* __restrict__ cams,
+                                                                   double* __restrict__ uv) {
+  extern __shared__ unsigned char pm_smem[];
+  ProjCam* sc = reinterpret_cast<ProjCam*>(pm_smem);
+  double* sp = reinterpret_cast<double*>(pm_smem + sizeof(ProjCam) * C);   // [256][3]
+  const double* src = cams ? reinterpret_cast<const double*>(cams) : reinterpret_cast<const double*>(&pack);
+  for (int i = threadIdx.x; i < C * (int)(sizeof(ProjCam) / sizeof(double)); i += blockDim.x)
+    reinterpret_cast<double*>(sc)[i] = src[i];
+  for (long long base = blockIdx.x * 256LL; base < P; base += gridDim.x * 256LL) {
+    const long long n_here = P - base < 256 ? P - base : 256;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * n_here; i += 256) sp[i] = pts[3 * base + i];
+    __syncthreads();
+    if (threadIdx.x < n_here) {
+      const double p[3] = {sp[3 * threadIdx.x], sp[3 * threadIdx.x + 1], sp[3 * threadIdx.x + 2]};
+      for (int c = 0; c < C; ++c) {
+        const ProjCam& cam = sc[c];
+        double X[3];
+        mat3_vec(cam.R, p, X);
+        X[0] += cam.t[0]; X[1] += cam.t[1]; X[2] += cam.t[2];
+        if (cam.has_dist) {
+          const double iz = 1.0 / X[2];   // one reciprocal per division pair: the pass is FP64-issue bound
+          const double xn = X[0] * iz, yn = X[1] * iz;
+          const double r2 = xn * xn + yn * yn;
+          const double d = 1.0 + cam.k1 * r2 + cam.k2 * (r2 * r2);
+          X[0] *= d;
+          X[1] *= d;
+        }
+        double h[3];
+        mat3_vec(cam.K, X, h);
+        const double ih = 1.0 / h[2];
+        reinterpret_cast<double2*>(uv)[(long long)c * P + base + threadIdx.x] = make_double2(h[0] * ih, h[1] * ih);
+      }
+    }
+  }
+}
+
 // X_w[f,n] = R(rho_f) X_o[n] + tau_f   (bundle_adjustment.py:27-29)
 __global__ void embed_points_kernel(const double* __restrict__ poses, long long F, const double* __restrict__ obj,
                                     int N, double* __restrict__ world) {
@@ -137,6 +184,95 @@ __device__ __forceinline__ void smallest_right_singular_vector(double A[4][4], d
   for (int i = 0; i < 4; ++i) out[i] = best == 0 ? V[i][0] : best == 1 ? V[i][1] : best == 2 ? V[i][2] : V[i][3];
 }
 
+// The same vector for the DLT systems of triangulation, ~10x cheaper: A = Q R (Householder), the
+// smallest right singular vector of A is that of R.  With one small singular value the null
+// direction sits in the last column: start from the back-substitution solution of R[:3,:3] y = -R[:3,3]
+// (exact when R33 = 0) and polish with inverse iteration on R^T R (two triangular solves per
+// step; error shrinks by (sigma_4 / sigma_3)^2 per step).  Returns false when the iteration has
+// not settled to 1e-13 after 8 steps (near-degenerate pair): the caller then runs the Jacobi SVD.
+__device__ __forceinline__ bool null_vector_qr(const double (&A0)[4][4], double out[4]) {
+  double R[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) R[i][j] = A0[i][j];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double nrm2 = 0.0;
+#pragma unroll
+    for (int i = k; i < 4; ++i) nrm2 = fma(R[i][k], R[i][k], nrm2);
+    const double alpha = -copysign(sqrt(nrm2), R[k][k]);
+    double v[4];
+#pragma unroll
+    for (int i = k; i < 4; ++i) v[i] = R[i][k];
+    v[k] -= alpha;
+    double vv = 0.0;
+#pragma unroll
+    for (int i = k; i < 4; ++i) vv = fma(v[i], v[i], vv);
+    if (vv > 0.0) {
+      const double beta = 2.0 / vv;
+#pragma unroll
+      for (int j = k + 1; j < 4; ++j) {
+        double d = 0.0;
+#pragma unroll
+        for (int i = k; i < 4; ++i) d = fma(v[i], R[i][j], d);
+        d *= beta;
+#pragma unroll
+        for (int i = k; i < 4; ++i) R[i][j] = fma(-d, v[i], R[i][j]);
+      }
+    }
+    R[k][k] = alpha;
+  }
+  const double scale = fabs(R[0][0]) + fabs(R[1][1]) + fabs(R[2][2]);
+  if (!(scale > 0.0) || !(scale < INFINITY)) return false;
+  if (fabs(R[0][0]) < 1e-12 * scale || fabs(R[1][1]) < 1e-12 * scale || fabs(R[2][2]) < 1e-12 * scale) return false;
+  double r33 = R[3][3];
+  if (fabs(r33) < 1e-300) r33 = 1e-300;
+  const double i0 = 1.0 / R[0][0], i1 = 1.0 / R[1][1], i2 = 1.0 / R[2][2], i3 = 1.0 / r33;
+  double y[4];
+  y[3] = 1.0;
+  y[2] = -(R[2][3]) * i2;
+  y[1] = -(R[1][2] * y[2] + R[1][3]) * i1;
+  y[0] = -(R[0][1] * y[1] + R[0][2] * y[2] + R[0][3]) * i0;
+  {
+    const double n = rsqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2] + 1.0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] *= n;
+  }
+  bool ok = false;
+  for (int it = 0; it < 8 && !ok; ++it) {
+    double z[4], w[4];
+    z[0] = y[0] * i0;                                               // R^T z = y
+    z[1] = (y[1] - R[0][1] * z[0]) * i1;
+    z[2] = (y[2] - R[0][2] * z[0] - R[1][2] * z[1]) * i2;
+    z[3] = (y[3] - R[0][3] * z[0] - R[1][3] * z[1] - R[2][3] * z[2]) * i3;
+    w[3] = z[3] * i3;                                               // R w = z
+    w[2] = (z[2] - R[2][3] * w[3]) * i2;
+    w[1] = (z[1] - R[1][2] * w[2] - R[1][3] * w[3]) * i1;
+    w[0] = (z[0] - R[0][1] * w[1] - R[0][2] * w[2] - R[0][3] * w[3]) * i0;
+    // scale first: w can be ~1/sigma_4^2
+    const double m = fmax(fmax(fabs(w[0]), fabs(w[1])), fmax(fabs(w[2]), fabs(w[3])));
+    if (!(m > 0.0) || !(m < INFINITY)) return false;
+    const double im = 1.0 / m;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] *= im;
+    double n = rsqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2] + w[3] * w[3]);
+    const double dot = w[0] * y[0] + w[1] * y[1] + w[2] * y[2] + w[3] * y[3];
+    if (dot < 0.0) n = -n;
+    double diff = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double wi = w[i] * n;
+      diff = fmax(diff, fabs(wi - y[i]));
+      y[i] = wi;
+    }
+    ok = it >= 1 && diff < 1e-13;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = y[i];
+  return ok;
+}
+
 __device__ __forceinline__ double nan_median(double* v, int n) {
   if (n == 0) return nan("");
   for (int i = 1; i < n; ++i) {  // insertion sort
@@ -182,7 +318,7 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const double* __restri
           A[3][k] = und[j][1] * Pj[8 + k] - Pj[4 + k];
         }
         double X[4];
-        smallest_right_singular_vector(A, X);
+        if (!null_vector_qr(A, X)) smallest_right_singular_vector(A, X);
         const double vx = X[0] / X[3], vy = X[1] / X[3], vz = X[2] / X[3];
         // np.nanmedian drops NaN entries per coordinate (geometry.py:432)
         px[np] = vx; py[np] = vy; pz[np] = vz;
@@ -240,6 +376,44 @@ int mcba_project_points(int device, void* stream, const double* d_points, int64_
   const int grid = (int)std::min<long long>((P + 255) / 256, 148 * 16);
   project_points_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_points, P, cam, d_uv);
   MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+int mcba_project_points_multi(int device, void* stream, const double* d_points, int64_t P, int C, const double* ext,
+                              const double* K, const double* dist, double* d_uv) {
+  if (!d_points || !ext || !K || !d_uv || P < 0 || C < 1 || C > 64) {
+    set_error("mcba_project_points_multi: bad arguments (1 <= n_cameras <= 64)");
+    return MCBA_ERR_ARG;
+  }
+  MCBA_CUDA(cudaSetDevice(device));
+  if (P == 0) return MCBA_OK;
+  { int rc = keep_async_pool(device); if (rc) return rc; }
+  static ProjCamPack pack;     // cameras 0..15 travel by value: no upload, no synchronisation
+  ProjCam cams_big[64];
+  ProjCam* cams = C <= kProjByValue ? pack.c : cams_big;
+  for (int c = 0; c < C; ++c) {
+    host_rodrigues(ext + 6 * c, cams[c].R);
+    for (int i = 0; i < 3; ++i) cams[c].t[i] = ext[6 * c + 3 + i];
+    for (int i = 0; i < 9; ++i) cams[c].K[i] = K[9 * c + i];
+    cams[c].has_dist = dist != nullptr;
+    cams[c].k1 = dist ? dist[2 * c] : 0.0;
+    cams[c].k2 = dist ? dist[2 * c + 1] : 0.0;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (int)std::min<long long>((P + 255) / 256, 148 * 8);
+  const size_t smem = sizeof(ProjCam) * C + sizeof(double) * 3 * 256;
+  if (C <= kProjByValue) {
+    project_points_multi_kernel<<<grid, 256, smem, s>>>(d_points, P, C, pack, nullptr, d_uv);
+    MCBA_CUDA(cudaGetLastError());
+    return MCBA_OK;
+  }
+  ProjCam* d_cams = nullptr;
+  MCBA_CUDA(cudaMallocAsync((void**)&d_cams, sizeof(ProjCam) * C, s));
+  MCBA_CUDA(cudaMemcpyAsync(d_cams, cams, sizeof(ProjCam) * C, cudaMemcpyHostToDevice, s));
+  project_points_multi_kernel<<<grid, 256, smem, s>>>(d_points, P, C, pack, d_cams, d_uv);
+  MCBA_CUDA(cudaGetLastError());
+  MCBA_CUDA(cudaStreamSynchronize(s));   // cams_big[] is a stack buffer
+  MCBA_CUDA(cudaFreeAsync(d_cams, s));
   return MCBA_OK;
 }
 

@@ -134,6 +134,34 @@ def project_points(points, extrinsics, camera_matrix, dist_coefs=None):
     return _native.to_host(d_uv).reshape(*lead, 2)
 
 
+def project_points_multi(points, all_extrinsics, all_intrinsics, _device_points=None):
+    """``np.stack([project_points(points, ext, K, dist) for ...])`` in one pass over the points
+    (``mcba_project_points_multi``): (...,3) -> (C,...,2).  ``all_intrinsics`` is the reference's
+    list of ``(camera_matrix, dist_coefs)``; every camera must either have distortion or not."""
+    torch, lib, dev = _device_ctx()
+    if _device_points is None:
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        lead = pts.shape[:-1]
+        d_pts = _native.to_device(pts.reshape(-1, 3), dev)
+    else:
+        d_pts, lead = _device_points
+    C = len(all_extrinsics)
+    ext = np.ascontiguousarray(np.stack([np.asarray(e, dtype=np.float64) for e in all_extrinsics]))
+    Ks = np.ascontiguousarray(np.stack([np.asarray(K, dtype=np.float64) for K, _ in all_intrinsics]))
+    has = [d is not None for _, d in all_intrinsics]
+    if any(has) != all(has):
+        raise ValueError("project_points_multi: dist_coefs must be given for every camera or for none")
+    dist = None
+    if all(has):
+        dist = np.ascontiguousarray(np.stack([np.asarray(d, dtype=np.float64).ravel()[:2] for _, d in all_intrinsics]))
+    d_uv = torch.empty((C, d_pts.shape[0], 2), dtype=torch.float64, device=d_pts.device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(lib.mcba_project_points_multi(dev, stream, ctypes.c_void_p(d_pts.data_ptr()), d_pts.shape[0], C,
+                                        _h(ext), _h(Ks), None if dist is None else _h(dist),
+                                        ctypes.c_void_p(d_uv.data_ptr())))
+    return _native.to_host(d_uv).reshape(C, *lead, 2)
+
+
 def undistort_points(uvs, camera_matrix, dist_coefs):
     """NaN-aware ``cv2.undistortPoints(uv, K, dist, None, K)`` (geometry.py:328-358)."""
     torch, lib, dev = _device_ctx()

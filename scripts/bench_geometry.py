@@ -56,6 +56,16 @@ def project_all():
                                               vp(dist[c, :2]), ctypes.c_void_p(d_uv[c].data_ptr())))
 
 
+def project_multi():
+    _native.check(lib.mcba_project_points_multi(dev, stream, ctypes.c_void_p(d_pts.data_ptr()), P, 6, vp(ext), vp(Ks),
+                                                vp(dist[:, :2]), ctypes.c_void_p(d_uv.data_ptr())))
+
+
+ms_m = timed(project_multi)
+out["project_points_multi"] = {"ms": ms_m, "views_per_s": 6 * P / (ms_m * 1e-3), "algorithmic_bytes": P * 24 + 6 * P * 16,
+                               "achieved_gbs": (P * 24 + 6 * P * 16) / (ms_m * 1e-3) / 1e9,
+                               "hbm_frac": (P * 24 + 6 * P * 16) / (ms_m * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                               "note": "one pass over the points for all 6 cameras"}
 ms = timed(project_all)
 out["project_points"] = {"ms": ms, "views_per_s": 6 * P / (ms * 1e-3), "algorithmic_bytes": 6 * P * (24 + 16),
                          "achieved_gbs": 6 * P * 40 / (ms * 1e-3) / 1e9}

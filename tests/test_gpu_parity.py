@@ -438,3 +438,19 @@ def test_device_transformation_vectors_match_reference():
         _native.check(lib.mcba_transformation_vectors(torch.cuda.current_device(), stream, ctypes.c_void_p(d_in.data_ptr()),
                                                       len(g[key]), dim, ctypes.c_void_p(d_out.data_ptr())))
         np.testing.assert_allclose(_native.to_host(d_out), g[f"{key}_vec"], rtol=0, atol=1e-12)
+
+
+def test_project_points_multi_matches_per_camera_projection():
+    g = load_golden("triangulate")
+    intr = list(zip(g["Ks"], g["dists"]))
+    rng = np.random.default_rng(4)
+    pts = rng.normal(0, 80, (3, 1001, 3))                       # leading dims, ragged against the 256-point blocks
+    both = mcc.project_points_multi(pts, list(g["extrinsics"]), intr)
+    assert both.shape == (len(intr), 3, 1001, 2)
+    for c, (ext, (K, dist)) in enumerate(zip(g["extrinsics"], intr)):
+        np.testing.assert_allclose(both[c], orc.project_points(pts, ext, K, dist), rtol=1e-12)
+        np.testing.assert_allclose(both[c], mcc.project_points(pts, ext, K, dist), rtol=1e-14)
+    nodist = mcc.project_points_multi(pts, list(g["extrinsics"]), [(K, None) for K, _ in intr])
+    np.testing.assert_allclose(nodist[2], orc.project_points(pts, g["extrinsics"][2], intr[2][0], None), rtol=1e-12)
+    with pytest.raises(ValueError):
+        mcc.project_points_multi(pts, list(g["extrinsics"]), [(K, None if c else d) for c, (K, d) in enumerate(intr)])
