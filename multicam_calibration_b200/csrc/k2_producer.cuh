@@ -38,7 +38,7 @@ struct K2PParams {
   const int* gprefix;         // [C + 1] groups of kWarps units before camera c; [C] = total
   const double* obj;          // (N,3)
   const double* x;            // 12C + 6F
-  const CamConst* cams;       // per-camera constants (prep_cameras_kernel)
+  CamConst* cams;             // per-camera constants: built by every CTA for itself, published by CTA 0 for K2c / finalize / K3
   double inv_c, c2;           // 1/f_scale, f_scale^2
   double* H;                  // [tile][c][63][32]
   double* partU;              // [grid][C][kAcc]
@@ -262,6 +262,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
   double* s_U = s_obj + ((3 * N + 1) & ~1);              // [C][kAcc]   CTA partial sums of U, g
   double* s_Uw = s_U + (size_t)C * kAcc;                 // [kWarps][kAcc] per-group staging
   double* s_R = s_Uw + (size_t)kWarps * kAcc;            // [kWarps][12][32] per-lane Rcf | tcf
+  CamConst* s_cam = reinterpret_cast<CamConst*>(s_R + (size_t)kWarps * 12 * 32);   // [C]
+  if (threadIdx.x < C) {   // camera constants in the kernel itself: no separate launch in front of the walk
+    const double* q = p.x + 12 * threadIdx.x;
+    CamConst k;
+    k.fx = q[0]; k.fy = q[1]; k.cx = q[2]; k.cy = q[3]; k.k1 = q[4]; k.k2 = q[5];
+    const double r[3] = {q[6], q[7], q[8]};
+    k.t[0] = q[9]; k.t[1] = q[10]; k.t[2] = q[11];
+    rodrigues(r, k.R);
+    so3_left_jacobian(r, k.Jl);
+    cross_mat3(k.t, k.Jl, k.tJ);
+    s_cam[threadIdx.x] = k;
+    if (blockIdx.x == 0) p.cams[threadIdx.x] = k;
+  }
   for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_obj[i] = p.obj[i];
   for (int i = threadIdx.x; i < C * kAcc; i += blockDim.x) s_U[i] = 0.0;
   double cost_acc = 0.0, sumsq_acc = 0.0, cnt_acc = 0.0;
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
     const int k = (g - p.gprefix[c]) * kWarps + warp;
     const bool live = k < p.unit_count[c];
     const long long tile = live ? p.units[(long long)c * p.nTiles + k] : 0;
-    const CamConst& cam = p.cams[c];
+    const CamConst& cam = s_cam[c];
     double* uw = s_Uw + warp * kAcc;
     if (live) {
       const long long f = p.perm[tile * kTile + lane];
@@ -368,7 +381,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
 }
 
 inline size_t k2p_smem(int C, int N, int warps) {
-  return sizeof(double) * (((3 * N + 1) & ~1) + (size_t)C * kAcc + (size_t)warps * kAcc + (size_t)warps * 12 * 32);
+  return sizeof(double) * (((3 * N + 1) & ~1) + (size_t)C * kAcc + (size_t)warps * kAcc + (size_t)warps * 12 * 32) +
+         sizeof(CamConst) * (size_t)C;
 }
 
 }  // namespace mcba

@@ -391,16 +391,17 @@ struct ReduceSeg {
   int n_part, len;
 };
 template <int kEl, int kPg>
-__global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceSeg s0, ReduceSeg s1, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceSeg s0, ReduceSeg s1, ReduceSeg s2,
+                                                              double* __restrict__ out) {
   static_assert(kEl * kPg == 256, "one thread per (element, partial group)");
   __shared__ double sm[kPg][kEl];
   const int el = threadIdx.x % kEl, pg = threadIdx.x / kEl;
   const int e = blockIdx.x * kEl + el;
   double v = 0.0;
-  const int total = s0.len + s1.len;
+  const int total = s0.len + s1.len + s2.len;
   if (e < total) {
-    const ReduceSeg sg = e < s0.len ? s0 : s1;
-    const double* src = sg.part + (e < s0.len ? e : e - s0.len);
+    const ReduceSeg sg = e < s0.len ? s0 : (e < s0.len + s1.len ? s1 : s2);
+    const double* src = sg.part + (e < s0.len ? e : (e < s0.len + s1.len ? e - s0.len : e - s0.len - s1.len));
     const int np = sg.n_part;
     const size_t stride = (size_t)sg.len;
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -431,11 +432,9 @@ int launch_finalize(mcba_handle* h) {
     // d_Sraw = [S (nc8^2) | U (C kAcc) | Z y (nc)]
     const ReduceSeg s0{h->d_partSyrk, h->grid_syrk, lenS};
     const ReduceSeg s1{h->d_partU, h->grid_frames, lenU};
-    reduce_partials_kernel<16, 16><<<(lenS + lenU + 15) / 16, 256, 0, h->stream>>>(s0, s1, h->d_Sraw);
-    const ReduceSeg z0{h->d_partZy, h->n_part_c, lenZy};
-    const ReduceSeg z1{nullptr, 0, 0};
-    reduce_partials_kernel<8, 32><<<(lenZy + 7) / 8, 256, 0, h->stream>>>(z0, z1, h->d_Sraw + lenS + lenU);
-    h->launches += 2;
+    const ReduceSeg s2{h->d_partZy, h->n_part_c, lenZy};   // one launch for all three segments
+    reduce_partials_kernel<16, 16><<<(lenS + lenU + lenZy + 15) / 16, 256, 0, h->stream>>>(s0, s1, s2, h->d_Sraw);
+    h->launches += 1;
     MCBA_CUDA(cudaGetLastError());
   }
   p.Sraw = h->d_Sraw;

@@ -71,9 +71,8 @@ static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, do
   int rc;
   const bool prof = h->profile && !redamp && h->prof_n < kProfRing;
   cudaEvent_t* ev = prof ? h->prof_ev + kProfEvents * h->prof_n : nullptr;
-  if ((rc = launch_prep_cameras(h, x))) return rc;   // also after a rejected step: the trial cost pass overwrote d_cams
   if (prof) cudaEventRecord(ev[0], h->stream);
-  if (!redamp) {
+  if (!redamp) {   // K2p also builds and publishes the camera constants of x (d_cams)
     if ((rc = launch_k2_producer(h, x, loss, f_scale))) return rc;
   }
   if (prof) cudaEventRecord(ev[1], h->stream);
@@ -480,7 +479,6 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
     // case) its hand-off is what K2c needs next -- no separate cost pass, no second walk.
     swap_k2p_outputs(h);
     const int trial_loss = loss_code();
-    if ((rc = launch_prep_cameras(h, xt))) return rc;
     if ((rc = launch_k2_producer(h, xt, trial_loss, opt.f_scale))) return rc;
     sum_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_partS, h->grid_frames, h->d_scal);
     h->launches++;
