@@ -308,6 +308,56 @@ def test_full_size_properties_cfg2():
     assert res.optimality < 1e-2 * np.abs(gcam).max()
 
 
+def test_full_size_properties_cfg3():
+    """BASELINE configs[2] at full size (6 cams x 50,000 frames, 20 % missing views, 0.5 px noise):
+    size-independent properties, no oracle at this size."""
+    C, F = 6, 50000
+    sc = make_scene(C, F, sigma=0.5, p_missing_view=0.2, seed=0)
+    prob = mcc.BAProblem(sc.uvs, sc.objpoints)
+    x0 = sc.x0()
+    nc = 12 * C
+    # (1) checksum of checksums: the cost accumulated inside K2p, the cost kernel and the robust
+    #     cost of the materialised residual vector agree; the vector has one entry per finite scalar
+    r = prob.residuals(x0)
+    assert r.size == (~np.isnan(sc.uvs)).sum() == prob.n_residuals
+    cost_r = float((2 * (np.sqrt(1 + r * r) - 1)).sum() * 0.5)
+    S, b, gcam, cost = prob.build_reduced(x0, lam=1e-3)
+    assert cost == pytest.approx(cost_r, rel=1e-11)
+    assert prob.cost(x0)[0] == pytest.approx(cost_r, rel=1e-11)
+    assert np.abs(S - S.T).max() <= 1e-12 * np.abs(S).max()
+    # (2) residuals = observed - predicted on the finite entries, in the reference's order
+    pred = prob.predict(x0)
+    assert pred.shape == sc.uvs.shape and not np.isnan(pred).any()
+    ok = ~np.isnan(sc.uvs)
+    assert np.abs((sc.uvs - pred)[ok] - r).max() <= 1e-10 * np.abs(r).max()
+    # (3) frame order does not matter: a random permutation of the frames (observations and
+    #     poses together) gives the same reduced camera system up to summation order
+    perm = np.random.default_rng(5).permutation(F)
+    xp = np.concatenate([x0[:nc], x0[nc:].reshape(F, 6)[perm].ravel()])
+    Sp, bp, gp_, costp = mcc.BAProblem(np.ascontiguousarray(sc.uvs[:, perm]), sc.objpoints).build_reduced(xp, lam=1e-3)
+    assert costp == pytest.approx(cost, rel=1e-12)
+    assert np.abs(Sp - S).max() <= 1e-10 * np.abs(S).max()
+    assert np.abs(bp - b).max() <= 1e-9 * np.abs(b).max()
+    # (4) additivity over frame shards (what the multi-GPU path relies on): four uneven shards
+    bounds = [0, 7, 12501, 31000, F]
+    Ssum, bsum, csum = 0.0, 0.0, 0.0
+    for a, e in zip(bounds[:-1], bounds[1:]):
+        xl = np.concatenate([x0[:nc], x0[nc + 6 * a:nc + 6 * e]])
+        Sl, bl, _, cl = mcc.BAProblem(sc.uvs[:, a:e], sc.objpoints).build_reduced(xl, lam=1e-3)
+        Ssum, bsum, csum = Ssum + Sl, bsum + bl, csum + cl
+    assert csum == pytest.approx(cost, rel=1e-12)
+    assert np.abs(Ssum - S).max() <= 1e-10 * np.abs(S).max()
+    assert np.abs(bsum - b).max() <= 1e-9 * np.abs(b).max()
+    # (5) the solve ends at a stationary point at the noise floor, and solving again from there is idempotent
+    x, res = prob.solve(x0, ftol=1e-10, xtol=1e-10, verbose=0)
+    assert res.success and res.cost < cost
+    assert 0.48 < res.rms < 0.52          # sigma = 0.5 px
+    assert res.optimality < 1e-6 * np.abs(gcam).max()
+    x2, res2 = prob.solve(x, ftol=1e-10, xtol=1e-10, verbose=0)
+    assert res2.iterations <= 2 and abs(res2.cost - res.cost) <= 1e-9 * res.cost
+    assert np.abs(x2 - x).max() <= 1e-4   # the 6-D rigid gauge is free (as in the reference): a restart may drift along it
+
+
 # ------------------------------------------------------------------ device front end (SURVEY 8(f) N1)
 @pytest.mark.parametrize("threshold", [None, 2.5])
 def test_select_frames_device_matches_oracle(threshold, capsys):
