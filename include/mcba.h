@@ -146,6 +146,14 @@ int mcba_gradient(mcba_handle* h, double* d_grad);
  * all-reduced (NCCL).  id is the 128-byte ncclUniqueId made on rank 0. */
 int mcba_comm_unique_id(void* id128);
 int mcba_comm_init(mcba_handle* h, const void* id128, int rank, int nranks);
+/* One-shot all-reduce over NVLink peer memory (one process per GPU of one node): every rank
+ * exports the CUDA IPC handle (64 bytes) of its exchange buffer, the host side gathers the handles
+ * of all ranks (rank order) and hands them back; from then on the reduced-system and step-scalar
+ * sums run as ONE kernel that pushes into every peer's buffer and adds the slots in rank order
+ * (bit-identical on all ranks) instead of a library all-reduce.  Without these two calls the
+ * NCCL communicator of mcba_comm_init is used. */
+int mcba_comm_ipc_export(mcba_handle* h, int rank, int nranks, void* handle64);
+int mcba_comm_ipc_open(mcba_handle* h, const void* handles64 /* nranks x 64 bytes, rank order */);
 
 /* Front end of bundle_adjust on the device (bundle_adjustment.py:265-285): frame eligibility
  * (> 1 camera with a complete detection, :266), per-point reprojection errors of the initial

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "mcba_lm_run": (_I, [_P, _P, ctypes.POINTER(Options), ctypes.POINTER(Result), _P]),
     "mcba_comm_unique_id": (_I, [_P]),
     "mcba_comm_init": (_I, [_P, _P, _I, _I]),
+    "mcba_comm_ipc_export": (_I, [_P, _I, _I, _P]),
+    "mcba_comm_ipc_open": (_I, [_P, _P]),
     "mcba_project_points": (_I, [_I, _P, _P, _L, _P, _P, _P, _P]),
     "mcba_project_points_multi": (_I, [_I, _P, _P, _L, _I, _P, _P, _P, _P]),
     "mcba_embed_points": (_I, [_I, _P, _P, _L, _P, _I, _P]),

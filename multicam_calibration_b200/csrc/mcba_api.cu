@@ -50,7 +50,9 @@ static int load_nccl() {
 }
 
 int allreduce_packed(mcba_handle* h, double* buf, long long n) {
-  if (h->nranks <= 1 || !h->nccl_comm) return MCBA_OK;
+  if (h->nranks <= 1) return MCBA_OK;
+  if (h->peer_ready) return peer_allreduce(h, buf, n);   // one kernel over NVLink peer memory
+  if (!h->nccl_comm) return MCBA_OK;
   ncclResult_t r = g_nccl.AllReduce(buf, buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)h->nccl_comm, h->stream);
   if (r != ncclSuccess) {
     set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
@@ -276,6 +278,9 @@ int mcba_destroy(mcba_handle* h) {
   cudaSetDevice(h->device);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   if (h->solver) cusolverDnDestroy(h->solver);
+  for (int s = 0; s < kMaxRanks; ++s) if (h->peer_mapped[s]) cudaIpcCloseMemHandle(h->peer_mapped[s]);
+  if (h->peer_block) cudaFree(h->peer_block);
+  if (h->peer_counter) cudaFree(h->peer_counter);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
                   h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT};

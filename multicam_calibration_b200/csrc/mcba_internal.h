@@ -100,6 +100,15 @@ struct mcba_handle {
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer-memory all-reduce (mcba_peer.cu): exchange block = [flags 2 x kMaxRanks | slots 2 x nranks x cap]
+  void* peer_block = nullptr;
+  unsigned int* peer_counter = nullptr;
+  long long peer_cap = 0;
+  double* peer_slots[mcba::kMaxRanks] = {};
+  unsigned long long* peer_flags[mcba::kMaxRanks] = {};
+  void* peer_mapped[mcba::kMaxRanks] = {};   // IPC mappings to close
+  unsigned long long peer_epoch = 0;
+  bool peer_ready = false;
   long long launches = 0;  // kernels launched by this handle (bench gpu_launches)
   // optional per-kernel timing (CUDA events on the launching stream; bench.py roofline)
   bool profile = false;
@@ -120,6 +129,7 @@ void set_error(const std::string& msg);
   } while (0)
 
 int keep_async_pool(int device);   // k0_frontend.cu
+int peer_allreduce(mcba_handle* h, double* buf, long long n);   // mcba_peer.cu
 
 // kernel launchers (defined in the .cu files)
 int launch_prep_cameras(mcba_handle* h, const double* x);

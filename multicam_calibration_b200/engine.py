@@ -155,7 +155,25 @@ class BAProblem:
             buf = ctypes.create_string_buffer(bytes(uid), 128)
             check(self.lib.mcba_comm_init(self._h, buf, int(rank), int(world)))
             self.rank, self.world = int(rank), int(world)
+            self._open_peer_memory()
         self.set_observations(uvs, obj)
+
+    def _open_peer_memory(self):
+        """Exchange buffers of all ranks mapped through CUDA IPC (handles gathered with
+        torch.distributed): the per-evaluation sums then run as one kernel over NVLink peer memory
+        (csrc/mcba_peer.cu).  ``MCBA_NO_PEER=1`` keeps the NCCL all-reduce (A/B measurements)."""
+        import os
+        import torch.distributed as dist
+        self.peer_memory = False
+        if self.world <= 1 or os.environ.get("MCBA_NO_PEER") or not (dist.is_available() and dist.is_initialized()):
+            return
+        mine = ctypes.create_string_buffer(64)
+        check(self.lib.mcba_comm_ipc_export(self._h, self.rank, self.world, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw))
+        check(self.lib.mcba_comm_ipc_open(self._h, ctypes.create_string_buffer(b"".join(handles), 64 * self.world)))
+        dist.barrier()          # every rank has mapped every buffer before the first push
+        self.peer_memory = True
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
