@@ -140,11 +140,17 @@ static int ensure_alt_outputs(mcba_handle* h) {
   return MCBA_OK;
 }
 
-static int read_eval(mcba_handle* h, EvalOut* out) {
+// The scalars of the last evaluation ([b | g | diag | scalars | rank slots] of d_red) travel to the
+// pinned mirror asynchronously; parse_eval reads them after the caller's next synchronisation.
+static int enqueue_eval_readback(mcba_handle* h) {
   const Layout& L = h->L;
   const long long tail = L.redLen - L.offB;
   MCBA_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_red + L.offB, sizeof(double) * tail, cudaMemcpyDeviceToHost, h->stream));
-  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  return MCBA_OK;
+}
+
+static void parse_eval(mcba_handle* h, EvalOut* out) {
+  const Layout& L = h->L;
   const double* t = h->h_pinned;
   const double* g = t + (L.offG - L.offB);
   const double* sc = t + (L.offScal - L.offB);
@@ -158,6 +164,13 @@ static int read_eval(mcba_handle* h, EvalOut* out) {
   out->sumsq = sc[kRsSumSq];
   out->count = sc[kRsCount];
   out->gnorm = bad ? NAN : gn;
+}
+
+static int read_eval(mcba_handle* h, EvalOut* out) {
+  int rc = enqueue_eval_readback(h);
+  if (rc) return rc;
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  parse_eval(h, out);
   return MCBA_OK;
 }
 
@@ -475,6 +488,24 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
   if (opt.iter_callback) opt.iter_callback(opt.callback_user, 0, nfev, cost, NAN, NAN, ev.gnorm);
   if (ev.gnorm < opt.gtol) status = 1;
 
+  // One host synchronisation per iteration: the scalars of the evaluation at the accepted point
+  // are read back together with the NEXT trial's scalars (the trial is enqueued right behind the
+  // evaluation, nothing in it depends on the host), so the GPU never idles on a host round trip
+  // between the two halves of an iteration.  `pending` = an evaluation whose scalars are still
+  // on their way; its iteration line is reported when they arrive.
+  const long long trial_off = (L.redLen - L.offB) + 8;   // pinned mirror: [evaluation tail | trial scalars | info]
+  bool pending = false;
+  double last_rel_reduction = 1.0;
+  double pend_reduction = NAN, pend_step = NAN;
+  int pend_term = -2;
+  auto settle = [&]() {   // the pending evaluation's scalars have arrived
+    parse_eval(h, &ev);
+    cost = ev.cost;
+    if (opt.iter_callback) opt.iter_callback(opt.callback_user, iter, nfev, cost, pend_reduction, pend_step, ev.gnorm);
+    pending = false;
+    if (pend_term != -2) status = pend_term;
+    else if (ev.gnorm < opt.gtol) status = 1;
+  };
   while (status == -2) {
     if (nfev >= max_nfev) { status = 0; break; }
     if ((rc = solve_reduced(h, lambda))) return rc;
@@ -483,18 +514,28 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
     // outputs: its partial sums give the trial cost, and when the step is accepted (the common
     // case) its hand-off is what K2c needs next -- no separate cost pass, no second walk.
     swap_k2p_outputs(h);
-    const int trial_loss = loss_code();
+    // Which Gauss-Newton weights the trial walk accumulates only matters if the step is accepted.
+    // The IRLS -> Triggs switch happens when a step reduces the cost by < 1 %; once the previous
+    // step was below 10 % that is the likely outcome, so the trial is walked with Triggs weights
+    // already (a wrong guess costs the second walk that a blind trial would always pay).
+    const bool guess_switch = irls && opt.hessian == MCBA_HESSIAN_AUTO && last_rel_reduction < 0.1;
+    const int trial_loss = guess_switch ? (opt.loss & 0xff) : loss_code();
     if ((rc = launch_k2_producer(h, xt, trial_loss, opt.f_scale))) return rc;
     sum_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_partS, h->grid_frames, h->d_scal);
     h->launches++;
     if ((rc = allreduce_packed(h, h->d_scal, 12))) return rc;
-    MCBA_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_scal, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
-    MCBA_CUDA(cudaMemcpyAsync(h->h_pinned + 16, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    double* hp = h->h_pinned + trial_off;
+    MCBA_CUDA(cudaMemcpyAsync(hp, h->d_scal, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
+    MCBA_CUDA(cudaMemcpyAsync(hp + 16, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
     MCBA_CUDA(cudaStreamSynchronize(h->stream));
+    if (pending) {
+      settle();
+      if (status != -2) { swap_k2p_outputs(h); break; }   // converged at the current point: drop the trial
+    }
     ++nfev;
-    const double cost_new = h->h_pinned[0];
-    const double dd = h->h_pinned[8], xx = h->h_pinned[9], gd = h->h_pinned[10], dDd = h->h_pinned[11];
-    const int info = reinterpret_cast<const int*>(h->h_pinned + 16)[0];
+    const double cost_new = hp[0];
+    const double dd = hp[8], xx = hp[9], gd = hp[10], dDd = hp[11];
+    const int info = reinterpret_cast<const int*>(hp + 16)[0];
     const bool solve_ok = info == 0 && std::isfinite(cost_new) && std::isfinite(dd);
     const double pred = -0.5 * gd + 0.5 * lambda * dDd;
     const double actual = cost - cost_new;
@@ -515,18 +556,22 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       nu = 2.0;
       ++iter;
       if (irls && opt.hessian == MCBA_HESSIAN_AUTO && actual < 1e-2 * cost) irls = false;
+      last_rel_reduction = actual / cost;
       if (loss_code() != trial_loss) {   // the Gauss-Newton weights change here (once per solve): walk again
         if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;
       } else {
         if ((rc = evaluate_tail(h, x, lambda))) return rc;
       }
-      if ((rc = read_eval(h, &ev))) return rc;
+      if ((rc = enqueue_eval_readback(h))) return rc;
       ++njev;
-      const double cost_prev = cost;
-      cost = ev.cost;
-      if (opt.iter_callback) opt.iter_callback(opt.callback_user, iter, nfev, cost, cost_prev - cost, sn, ev.gnorm);
-      if (term != -2) status = term;
-      else if (ev.gnorm < opt.gtol) status = 1;
+      pending = true;
+      pend_reduction = actual;
+      pend_step = sn;
+      pend_term = term;
+      if (term != -2) {   // the step met ftol / xtol: finish with the evaluation at the new point
+        MCBA_CUDA(cudaStreamSynchronize(h->stream));
+        settle();
+      }
     } else {
       swap_k2p_outputs(h);   // back to the outputs of the current point
       if (term == 3 || term == 4) { status = 3; break; }   // step too small to matter (xtol)
@@ -534,8 +579,14 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       nu *= 2.0;
       if (lambda > opt.lambda_max) { status = -1; set_error("damping exceeded lambda_max without finding a descent step"); break; }
       if ((rc = evaluate_tail(h, x, lambda))) return rc;   // pose damping is baked into Z: K2c + SYRK only
-      if ((rc = read_eval(h, &ev))) return rc;
+      // same point, same cost and gradient: nothing to read back
     }
+  }
+  if (pending) {   // left the loop (budget / xtol) with an evaluation still in flight
+    MCBA_CUDA(cudaStreamSynchronize(h->stream));
+    const int keep = status;
+    settle();
+    status = keep;
   }
 
   MCBA_CUDA(cudaMemcpyAsync(d_x, x, sizeof(double) * n_local, cudaMemcpyDeviceToDevice, h->stream));
