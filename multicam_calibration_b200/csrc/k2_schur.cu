@@ -2,6 +2,8 @@
 // axis), the finalisation of the packed reduced camera system in the true
 // parameter basis, the damped Cholesky solve and K3, the pose back-substitution.
 // Math: SURVEY.md Appendix A ("Schur form for this problem").
+#include <cstdlib>
+
 #include "k2_common.cuh"
 
 namespace mcba {
@@ -97,7 +99,95 @@ __device__ __forceinline__ void syrk_stage(const double* __restrict__ st, const 
   }
 }
 
-template <int kSyrkWarps>
+// ---- compile-time tile lists (common camera counts): which 8x8 tiles a warp owns is then known
+// to the compiler, so the A fragment of a row block is loaded ONCE per run of tiles that share it
+// and a diagonal tile reuses it as its B fragment -- plain straight-line code, no run-time masks
+// (those were measured slower, scripts/experiments/README.md).  The fragment loads are what bounds
+// the SYRK (shared-memory bandwidth): ~7 instead of 12 per k-step at 6 cameras.
+__host__ __device__ constexpr int st_tile_i(int t, int nb8) {
+  int I = 0, rem = t;
+  while (I < nb8 - 1 && rem >= nb8 - I) { rem -= nb8 - I; ++I; }
+  return I;
+}
+__host__ __device__ constexpr int st_tile_j(int t, int nb8) {
+  int I = 0, rem = t;
+  while (I < nb8 - 1 && rem >= nb8 - I) { rem -= nb8 - I; ++I; }
+  return I + rem;
+}
+template <int kW, int NB8, int WARP>
+struct StaticTiles {   // mirrors syrk_tile_range for gridDim.y == 1
+  static constexpr int nT = NB8 * (NB8 + 1) / 2;
+  static constexpr int base = nT / kW, extra = nT % kW, first_big = kW - extra;
+  static constexpr int cnt = base + (WARP >= first_big ? 1 : 0);
+  static constexpr int t0 = WARP * base + (WARP > first_big ? WARP - first_big : 0);
+};
+
+template <int kW, int NB8, int WARP, int SL>
+struct StaticStep {
+  using T = StaticTiles<kW, NB8, WARP>;
+  static __device__ __forceinline__ void run(const double* __restrict__ st, int ld8, double& a,
+                                             double (&acc)[kSyrkSlots][2]) {
+    if constexpr (SL < T::cnt) {
+      constexpr int t = T::t0 + SL;
+      constexpr int I = st_tile_i(t, NB8), J = st_tile_j(t, NB8);
+      constexpr int Iprev = SL > 0 ? st_tile_i(t - 1, NB8) : -1;
+      if constexpr (I != Iprev) a = st[I * ld8];
+      double b = a;
+      if constexpr (I != J) b = st[J * ld8];
+      dmma_m8n8k4(acc[SL][0], acc[SL][1], a, b);
+      StaticStep<kW, NB8, WARP, SL + 1>::run(st, ld8, a, acc);
+    }
+  }
+  static __device__ __forceinline__ void store(double* __restrict__ out, int nc8, int lane,
+                                               const double (&acc)[kSyrkSlots][2]) {
+    if constexpr (SL < T::cnt) {
+      constexpr int t = T::t0 + SL;
+      constexpr int I = st_tile_i(t, NB8), J = st_tile_j(t, NB8);
+      *reinterpret_cast<double2*>(out + (size_t)(I * 8 + (lane >> 2)) * nc8 + J * 8 + 2 * (lane & 3)) =
+          make_double2(acc[SL][0], acc[SL][1]);
+      StaticStep<kW, NB8, WARP, SL + 1>::store(out, nc8, lane, acc);
+    }
+  }
+};
+
+// the whole consumer loop of one warp with a compile-time tile list
+template <int kW, int NB8, int WARP>
+__device__ __forceinline__ void syrk_consume_static(const SyrkParams& p, const double* stages, size_t stage_doubles,
+                                                    int ld, int n_units, unsigned long long* full_bar,
+                                                    unsigned long long* empty_bar, int lane) {
+  using T = StaticTiles<kW, NB8, WARP>;
+  constexpr int kUnroll = T::cnt <= 6 ? 8 : (T::cnt <= 12 ? 2 : 1);
+  double acc[kSyrkSlots][2];
+#pragma unroll
+  for (int s = 0; s < kSyrkSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
+  const int lane_off = (lane >> 2) * ld + (lane & 3);
+  const int ld8 = 8 * ld;
+  for (int unit = 0; unit < n_units; ++unit) {
+    const int s = unit % kSyrkStages;
+    mbar_wait(&full_bar[s], (unsigned)((unit / kSyrkStages) & 1));
+    const double* st = stages + (size_t)s * stage_doubles + lane_off;
+#pragma unroll kUnroll
+    for (int k0 = 0; k0 < p.KW; k0 += 4) {
+      double a = 0.0;
+      StaticStep<kW, NB8, WARP, 0>::run(st + k0, ld8, a, acc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+  StaticStep<kW, NB8, WARP, 0>::store(p.part + (size_t)blockIdx.x * p.nc8 * p.nc8, p.nc8, lane, acc);
+}
+
+template <int kW, int NB8, int WARP = 0>
+__device__ __forceinline__ void syrk_dispatch_static(int warp, const SyrkParams& p, const double* stages,
+                                                     size_t stage_doubles, int ld, int n_units,
+                                                     unsigned long long* full_bar, unsigned long long* empty_bar, int lane) {
+  if constexpr (WARP < kW) {
+    if (warp == WARP) syrk_consume_static<kW, NB8, WARP>(p, stages, stage_doubles, ld, n_units, full_bar, empty_bar, lane);
+    else syrk_dispatch_static<kW, NB8, WARP + 1>(warp, p, stages, stage_doubles, ld, n_units, full_bar, empty_bar, lane);
+  }
+}
+
+template <int kSyrkWarps, int NB8 = 0>
 __global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const SyrkParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ unsigned long long full_bar[kSyrkStages], empty_bar[kSyrkStages];
@@ -138,6 +228,10 @@ __global__ void __launch_bounds__((kSyrkWarps + 1) * 32, 1) k2_syrk_kernel(const
     return;
   }
 
+  if constexpr (NB8 > 0) {   // compile-time tile lists (gridDim.y == 1)
+    syrk_dispatch_static<kSyrkWarps, NB8>(warp, p, stages, stage_doubles, ld, n_units, full_bar, empty_bar, lane);
+    return;
+  }
   // ---------------- consumers: up to 12 tiles of the upper block triangle per warp ----------------
   int t0, cnt;
   syrk_tile_range<kSyrkWarps>(p, warp, t0, cnt);
@@ -241,13 +335,31 @@ int launch_k2_syrk(mcba_handle* h) {
   p.nTiles = (int)L.nTiles;
   p.KW = c.KW;
   p.part = h->d_partSyrk;
+  static const bool no_static = getenv("MCBA_SYRK_RUNTIME") != nullptr;   // A/B: run-time tile lists
+#define MCBA_SYRK(W, NB)                                                                                          \
+  do {                                                                                                            \
+    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<W, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem)); \
+    k2_syrk_kernel<W, NB><<<dim3(h->grid_syrk, c.gy), (W + 1) * 32, c.smem, h->stream>>>(p);                      \
+  } while (0)
+  const int nb = (c.gy == 1 && !no_static) ? p.nb8 : 0;
   if (c.warps == 8) {
-    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    k2_syrk_kernel<8><<<dim3(h->grid_syrk, c.gy), 9 * 32, c.smem, h->stream>>>(p);
+    switch (nb) {
+      case 3: MCBA_SYRK(8, 3); break;    // 2 cameras
+      case 5: MCBA_SYRK(8, 5); break;    // 3
+      case 6: MCBA_SYRK(8, 6); break;    // 4
+      case 8: MCBA_SYRK(8, 8); break;    // 5
+      case 9: MCBA_SYRK(8, 9); break;    // 6
+      case 12: MCBA_SYRK(8, 12); break;  // 8
+      default: MCBA_SYRK(8, 0); break;
+    }
   } else {
-    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-    k2_syrk_kernel<15><<<dim3(h->grid_syrk, c.gy), 16 * 32, c.smem, h->stream>>>(p);
+    switch (nb) {
+      case 18: MCBA_SYRK(15, 18); break;  // 12 cameras
+      case 24: MCBA_SYRK(15, 24); break;  // 16
+      default: MCBA_SYRK(15, 0); break;
+    }
   }
+#undef MCBA_SYRK
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
