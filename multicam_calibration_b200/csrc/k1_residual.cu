@@ -586,7 +586,7 @@ int launch_predict(mcba_handle* h, const double* x, double* uv_out) {
 }
 
 // ---------------------------------------------------------------- robust cost
-// warp per (tile, camera), lane = frame, tiled SoA (same stream as K2a without the Jacobian)
+// warp per (tile, camera), lane = frame, tiled SoA (the walk of K2p without the Jacobian); C ABI mcba_cost
 __global__ void __launch_bounds__(256) cost_kernel(const double* __restrict__ x, const double2* __restrict__ obs,
                                                    const double* __restrict__ obj, const CamConst* __restrict__ cams,
                                                    const int* __restrict__ perm, const unsigned int* __restrict__ active,

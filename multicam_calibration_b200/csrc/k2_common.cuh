@@ -1,4 +1,4 @@
-// Device helpers shared by the K2a kernels (see k2_frames.cu for the math).
+// Device helpers shared by the K2 kernels (K2p, K2c, SYRK, finalize; see k2_frames.cu for the math).
 #pragma once
 #include "mcba_internal.h"
 #include "mcba_obs.cuh"
