@@ -200,7 +200,7 @@ def bundle_adjust(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints
         prob = _problem_for(_gather_frames_device(d_uvs, use_frames), calib_objpoints)
         del d_uvs
         x, result = prob.solve(x0, **opt_kwargs)
-        on_device = result["_lazy"].pop("fun")
+        on_device = result.pop_lazy("fun")
 
         def fun():   # result.fun on first access (bundle_adjustment.py:66-98 at the solution)
             try:

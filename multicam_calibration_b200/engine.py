@@ -31,16 +31,23 @@ class OptimizeResult(dict):
     host on first access only; the solve itself never waits for them."""
     __setattr__ = dict.__setitem__
 
+    def _lazy_fields(self):
+        try:
+            return object.__getattribute__(self, "_lazy_store")
+        except AttributeError:
+            object.__setattr__(self, "_lazy_store", {})
+            return object.__getattribute__(self, "_lazy_store")
+
     def set_lazy(self, name, thunk):
-        lazy = dict.get(self, "_lazy")
-        if lazy is None:
-            lazy = {}
-            dict.__setitem__(self, "_lazy", lazy)
-        lazy[name] = thunk
+        self._lazy_fields()[name] = thunk
         dict.pop(self, name, None)
 
+    def pop_lazy(self, name):
+        """Remove and return the thunk of a lazy field (to wrap it)."""
+        return self._lazy_fields().pop(name)
+
     def __missing__(self, name):
-        lazy = dict.get(self, "_lazy") or {}
+        lazy = self._lazy_fields()
         if name in lazy:
             value = lazy.pop(name)()
             dict.__setitem__(self, name, value)
@@ -60,10 +67,10 @@ class OptimizeResult(dict):
             return default
 
     def __contains__(self, name):
-        return dict.__contains__(self, name) or name in (dict.get(self, "_lazy") or {})
+        return dict.__contains__(self, name) or name in self._lazy_fields()
 
     def keys(self):
-        return [k for k in dict.keys(self) if k != "_lazy"] + list(dict.get(self, "_lazy") or {})
+        return list(dict.keys(self)) + list(self._lazy_fields())
 
     def __dir__(self):
         return list(self.keys())

@@ -143,3 +143,20 @@ def test_frame_sharding_world2_gloo():
         p.join(60)
         assert p.exitcode == 0
     assert err < 1e-12 and same
+
+
+def test_optimize_result_lazy_fields():
+    """result.fun-style lazy fields: computed once on first access, visible in keys(), never stored as dict items."""
+    calls = []
+    r = engine.OptimizeResult(x=1, cost=2.0)
+    r.set_lazy("fun", lambda: calls.append(1) or [1, 2, 3])
+    assert "fun" in r and "fun" in r.keys() and not dict.__contains__(r, "fun")
+    assert set(dict(r)) == {"x", "cost"}
+    assert r.fun == [1, 2, 3] and r["fun"] == [1, 2, 3] and calls == [1]
+    assert dict.__contains__(r, "fun")
+    assert r.missing is None and r.get("missing", 5) == 5
+    with pytest.raises(KeyError):
+        r["missing"]
+    t = engine.OptimizeResult(a=1)
+    t.set_lazy("fun", lambda: 7)
+    assert t.pop_lazy("fun")() == 7 and "fun" not in t
