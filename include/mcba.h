@@ -154,6 +154,9 @@ int mcba_comm_init(mcba_handle* h, const void* id128, int rank, int nranks);
  * NCCL communicator of mcba_comm_init is used. */
 int mcba_comm_ipc_export(mcba_handle* h, int rank, int nranks, void* handle64);
 int mcba_comm_ipc_open(mcba_handle* h, const void* handles64 /* nranks x 64 bytes, rank order */);
+/* Switch between the peer-memory kernel and the NCCL all-reduce (all ranks must agree: the host
+ * side turns the peer path off everywhere when any rank failed to map a buffer). */
+int mcba_comm_ipc_enable(mcba_handle* h, int enable);
 
 /* Front end of bundle_adjust on the device (bundle_adjustment.py:265-285): frame eligibility
  * (> 1 camera with a complete detection, :266), per-point reprojection errors of the initial

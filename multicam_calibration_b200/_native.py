@@ -70,6 +70,7 @@ _SIGNATURES = {
     "mcba_comm_init": (_I, [_P, _P, _I, _I]),
     "mcba_comm_ipc_export": (_I, [_P, _I, _I, _P]),
     "mcba_comm_ipc_open": (_I, [_P, _P]),
+    "mcba_comm_ipc_enable": (_I, [_P, _I]),
     "mcba_project_points": (_I, [_I, _P, _P, _L, _P, _P, _P, _P]),
     "mcba_project_points_multi": (_I, [_I, _P, _P, _L, _I, _P, _P, _P, _P]),
     "mcba_embed_points": (_I, [_I, _P, _P, _L, _P, _I, _P]),

@@ -165,4 +165,14 @@ int mcba_comm_ipc_open(mcba_handle* h, const void* handles64) {
   return MCBA_OK;
 }
 
+int mcba_comm_ipc_enable(mcba_handle* h, int enable) {
+  if (!h) return MCBA_ERR_ARG;
+  if (enable && !h->peer_slots[0]) {
+    set_error("mcba_comm_ipc_enable: the peer buffers are not mapped");
+    return MCBA_ERR_STATE;
+  }
+  h->peer_ready = enable != 0;
+  return MCBA_OK;
+}
+
 }  // extern "C"

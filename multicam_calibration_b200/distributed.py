@@ -96,6 +96,7 @@ def solve_sharded(uvs_used, calib_objpoints, x0, **opt_kwargs):
     prob = BAProblem(uvs_used[:, start:stop], calib_objpoints, device=dev, comm=(uid, r, W))
     try:
         x_loc, result = prob.solve(split_params(x0, C, start, stop), **opt_kwargs)
+        result["peer_memory"] = bool(getattr(prob, "peer_memory", False))
     finally:
         prob.close()
     nc = 12 * C

@@ -174,13 +174,27 @@ class BAProblem:
         self.peer_memory = False
         if self.world <= 1 or os.environ.get("MCBA_NO_PEER") or not (dist.is_available() and dist.is_initialized()):
             return
+        # every step is collective: a rank that cannot export / map still takes part in the gathers,
+        # and the peer path is used only if EVERY rank mapped every buffer (else all ranks keep NCCL)
+        import sys
         mine = ctypes.create_string_buffer(64)
-        check(self.lib.mcba_comm_ipc_export(self._h, self.rank, self.world, mine))
+        ok = self.lib.mcba_comm_ipc_export(self._h, self.rank, self.world, mine) == _native.MCBA_OK
+        if os.environ.get("MCBA_TEST_PEER_FAIL") == str(self.rank):   # tests: this rank pretends it cannot export
+            ok = False
         handles = [None] * self.world
-        dist.all_gather_object(handles, bytes(mine.raw))
-        check(self.lib.mcba_comm_ipc_open(self._h, ctypes.create_string_buffer(b"".join(handles), 64 * self.world)))
-        dist.barrier()          # every rank has mapped every buffer before the first push
-        self.peer_memory = True
+        dist.all_gather_object(handles, (ok, bytes(mine.raw)))
+        ok = all(h[0] for h in handles)
+        if ok:
+            blob = ctypes.create_string_buffer(b"".join(h[1] for h in handles), 64 * self.world)
+            ok = self.lib.mcba_comm_ipc_open(self._h, blob) == _native.MCBA_OK
+        votes = [None] * self.world
+        dist.all_gather_object(votes, bool(ok))          # also: every rank has mapped before the first push
+        self.peer_memory = all(votes)
+        if not self.peer_memory:
+            self.lib.mcba_comm_ipc_enable(self._h, 0)
+            if self.rank == 0:
+                print("multicam_calibration_b200: CUDA IPC peer buffers unavailable "
+                      f"({self.lib.mcba_last_error().decode(errors='replace')}); using the NCCL all-reduce", file=sys.stderr)
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

@@ -30,7 +30,7 @@ if rank == 0:
     d_x = np.abs(xs - res.x).max()
     print(f"world={world} frames={len(use)} sharded: cost {res.cost:.9f} it {res.iterations} rms {res.rms:.9f} | "
           f"single: cost {rs.cost:.9f} it {rs.iterations} | rel dcost {d_cost:.2e} drms {d_rms:.2e} max|dx| {d_x:.2e} "
-          f"shard0 {res.shard} solve_ms {res.solve_ms:.2f} vs {rs.solve_ms:.2f}")
+          f"shard0 {res.shard} solve_ms {res.solve_ms:.2f} vs {rs.solve_ms:.2f} peer_memory={res.peer_memory}")
     ok = d_cost < 1e-9 and d_rms < 1e-8 and res.x.shape == xs.shape and res.success
     print("MULTIGPU_OK" if ok else "MULTIGPU_FAIL")
 dist.barrier()
