@@ -253,6 +253,69 @@ __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& 
   }
 }
 
+// The same walk for a HALF unit (16 frames): lanes 0-15 take the first half of the corners of
+// their frame, lanes 16-31 the second half of the same frames; the two partial blocks are added
+// with one shuffle pass afterwards.  Used for the units left over after the last full round of the
+// static schedule, which would otherwise cost every CTA a whole extra round for a fraction of the
+// warps (6.36 units per warp -> 7 rounds at BASELINE configs[2]).
+__host__ __device__ constexpr bool acc_slot_used(int i) { return i < 21 || (i >= 32 && i < 53) || (i >= 64 && i < 108); }
+
+template <int kLoss>
+__device__ __forceinline__ void walk_corners_half(const K2PParams& p, const IntrReg& cam, SrPtr sR,
+                                                  const double2* __restrict__ ob, const double* __restrict__ s_obj,
+                                                  int lane, double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
+                                                  double& cnt_acc) {
+  const int N = p.N, Nh = (N + 1) >> 1;
+  const int n0 = (lane & 16) ? Nh : 0;
+  const double2 missing = make_double2(nan(""), nan(""));
+  auto obs_at = [&](int n) { return n < N ? ob[(size_t)n * kTile] : missing; };
+  auto corner = [&](int n) { return n < N ? n : N - 1; };
+  double2 o0 = obs_at(n0);
+  double2 o1 = obs_at(n0 + 1);
+  double iz_next = inverse_depth(sR, s_obj[3 * corner(n0)], s_obj[3 * corner(n0) + 1], s_obj[3 * corner(n0) + 2]);
+#pragma unroll 1
+  for (int i = 0; i < Nh; ++i) {
+    const int n = corner(n0 + i), nn = corner(n0 + i + 1);
+    const double2 cur = o0;
+    o0 = o1;
+    o1 = obs_at(n0 + i + 2);
+    const double iz = iz_next;
+    iz_next = inverse_depth(sR, s_obj[3 * nn], s_obj[3 * nn + 1], s_obj[3 * nn + 2]);
+    Proj pr;
+    project_shared(cam, sR, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], iz, pr);
+    {
+      const bool hu = cur.x == cur.x;
+      const double fu = hu ? cur.x - pr.pu : 0.0;
+      double rho, wg, wh, au[10];
+      robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wh);
+      jac_row<true>(cam, pr, au);
+      cost_acc += rho;
+      sumsq_acc = fma(fu, fu, sumsq_acc);
+      cnt_acc += hu ? 1.0 : 0.0;
+      accumulate_row<true>(acc, au, wh, -wg * fu);
+    }
+    {
+      const bool hv = cur.y == cur.y;
+      const double fv = hv ? cur.y - pr.pv : 0.0;
+      double rho, wg, wh, av[10];
+      robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wh);
+      jac_row<false>(cam, pr, av);
+      cost_acc += rho;
+      sumsq_acc = fma(fv, fv, sumsq_acc);
+      cnt_acc += hv ? 1.0 : 0.0;
+      accumulate_row<false>(acc, av, wh, -wg * fv);
+    }
+  }
+  // add the two corner halves; lanes 16-31 then carry zeros so that the lane reductions count once
+#pragma unroll
+  for (int i = 0; i < kAcc; ++i) {
+    if (acc_slot_used(i)) {
+      const double other = __shfl_xor_sync(0xffffffffu, acc[i], 16);
+      acc[i] = (lane & 16) ? 0.0 : acc[i] + other;
+    }
+  }
+}
+
 template <int kLoss, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) {
   extern __shared__ double smem[];
@@ -284,8 +347,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
   // contiguous range of camera-major groups of live units for this CTA (all CTAs get the same
   // number of fully populated groups: static, balanced, and the partial sums stay deterministic)
   const int nGroups = p.gprefix[C];
-  const int g_begin = (int)(((long long)nGroups * blockIdx.x) / gridDim.x);
-  const int g_end = (int)(((long long)nGroups * (blockIdx.x + 1)) / gridDim.x);
+  // Leftover of the last full round: when at most half a round of groups remains and they belong
+  // to one camera, every CTA runs `rounds` full groups and the leftover units are split into half
+  // units (16 frames, corners divided over the two half-warps) spread over ALL CTAs.
+  const int rounds = nGroups / (int)gridDim.x, left_groups = nGroups - rounds * (int)gridDim.x;
+  int tail_c = 0;
+  while (tail_c + 1 < C && p.gprefix[tail_c + 1] <= rounds * (int)gridDim.x) ++tail_c;
+  const int tail_k0 = (rounds * (int)gridDim.x - p.gprefix[tail_c]) * kWarps;        // first leftover unit of camera tail_c
+  const int tail_units = left_groups > 0 ? p.unit_count[tail_c] - tail_k0 : 0;
+  const int tail_per_cta = (2 * tail_units + (int)gridDim.x - 1) / (int)gridDim.x;   // half units per CTA
+  const bool split_tail = kWarps == 8 && rounds >= 1 && left_groups > 0 && tail_per_cta <= kWarps &&
+                          p.gprefix[tail_c + 1] >= nGroups;
+  const int g_begin = split_tail ? rounds * (int)blockIdx.x : (int)(((long long)nGroups * blockIdx.x) / gridDim.x);
+  const int g_end = split_tail ? rounds * ((int)blockIdx.x + 1) : (int)(((long long)nGroups * (blockIdx.x + 1)) / gridDim.x);
   int c = 0;
   for (int g = g_begin; g < g_end; ++g) {
     while (c + 1 < C && p.gprefix[c + 1] <= g) ++c;     // CTA-uniform
@@ -344,6 +418,68 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) s += s_Uw[w * kAcc + i];
       s_U[c * kAcc + i] = s;
+    }
+    __syncthreads();
+  }
+
+  if (split_tail) {
+    const int hu = (int)blockIdx.x * tail_per_cta + warp;
+    const bool live = warp < tail_per_cta && hu < 2 * tail_units;
+    const int cc = tail_c;
+    const CamConst& cam = s_cam[cc];
+    double* uw = s_Uw + warp * kAcc;
+    if (live) {
+      const long long tile = p.units[(long long)cc * p.nTiles + tail_k0 + (hu >> 1)];
+      const int slot = (hu & 1) * 16 + (lane & 15);          // this lane's frame slot of the tile
+      const long long f = p.perm[tile * kTile + slot];
+      const bool fvalid = f >= 0;
+      {
+        double pose[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
+        double Rp[9], Rcf[9], tcf[3];
+        rodrigues(pose, Rp);
+        mat3_mul(cam.R, Rp, Rcf);
+        mat3_vec(cam.R, pose + 3, tcf);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) sR[i * 32] = Rcf[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sR[(9 + i) * 32] = tcf[i] + cam.t[i];
+      }
+      __syncwarp();
+      const double2* ob = p.obs + ((size_t)(tile * C + cc) * N) * kTile + slot;
+      double* h = p.H + ((size_t)(tile * C + cc) * kHandoff) * kTile + slot;
+      double acc[kAcc];
+#pragma unroll
+      for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+      const IntrReg in{opaque(cam.fx), opaque(cam.fy), opaque(cam.cx), opaque(cam.cy), opaque(cam.k1), opaque(cam.k2)};
+      walk_corners_half<kLoss>(p, in, sR, ob, s_obj, lane, acc, cost_acc, sumsq_acc, cnt_acc);
+      uw[lane] = lane_transpose_sum32<0>(acc, lane);
+      uw[32 + lane] = lane_transpose_sum32<32>(acc, lane);
+      uw[64 + lane] = lane_transpose_sum32<64>(acc, lane);
+      uw[96 + lane] = lane_transpose_sum32<96>(acc, lane);
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) h[(size_t)(i * 6 + j) * kTile] = acc[acc_slot(i, 6 + j)];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int q = r; q < 6; ++q) h[(size_t)(36 + tri6(r, q)) * kTile] = acc[acc_slot(6 + r, 6 + q)];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) h[(size_t)(57 + r) * kTile] = acc[acc_slot_q(6 + r)];
+      }
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) uw[32 * b + lane] = 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kAcc; i += kWarps * 32) {
+      double s = s_U[cc * kAcc + i];
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += s_Uw[w * kAcc + i];
+      s_U[cc * kAcc + i] = s;
     }
     __syncthreads();
   }
