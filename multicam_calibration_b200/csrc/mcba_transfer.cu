@@ -19,7 +19,7 @@
 namespace mcba {
 namespace {
 
-constexpr int kWorkers = 6;
+constexpr int kWorkers = 8;
 constexpr size_t kChunk = 4u << 20;   // bytes per bounce buffer
 
 struct Lane {
