@@ -33,8 +33,8 @@ UNIT = "obs/s"
 CAMS, FRAMES, SIGMA, P_MISSING = 6, 50_000, 0.5, 0.2
 WORKLOAD = (f"{CAMS} cams x {FRAMES} frames/GPU x 35 corners, {int(P_MISSING * 100)}% missing detections, "
             f"sigma={SIGMA} px (BASELINE.json configs[2])")
-CPU_SAMPLE_FRAMES = 1000
-CPU_CONVERGE_FRAMES = 200    # scipy trf to convergence on this many frames: ~15 s of one host core
+CPU_SAMPLE_FRAMES = int(os.environ.get("MCBA_BENCH_SAMPLE_FRAMES", 1000))      # frames of the workload timed on the host per step
+CPU_CONVERGE_FRAMES = int(os.environ.get("MCBA_BENCH_CONVERGE_FRAMES", 200))   # scipy trf to convergence on this many frames: ~15 s of one host core
 ALG_FMA_PER_OBS = 250.0   # projection + Jacobian rows ~65, robust weights ~30, A_cf / q_cf accumulation ~150, bookkeeping ~5
 
 
@@ -211,6 +211,7 @@ def run_engine(args):
     from multicam_calibration_b200.engine import BAProblem
     from multicam_calibration_b200.synthetic import make_scene
 
+    _native.require_cuda()   # no CPU fallback: the engine arm needs a B200
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))

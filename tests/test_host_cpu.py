@@ -160,3 +160,41 @@ def test_optimize_result_lazy_fields():
     t = engine.OptimizeResult(a=1)
     t.set_lazy("fun", lambda: 7)
     assert t.pop_lazy("fun")() == 7 and "fun" not in t
+
+
+def _run_bench(*argv, env=None):
+    import subprocess
+    import sys
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *argv], capture_output=True, text=True,
+                          timeout=600, env=e)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference runs on host cores only and prints exactly one JSON line with the
+    contract's keys (small samples here; the defaults are sized for the GPU box's host)."""
+    import json
+    out = _run_bench("--impl", "reference", "--steps", "1", "--warmup", "0",
+                     env={"MCBA_BENCH_SAMPLE_FRAMES": "60", "MCBA_BENCH_CONVERGE_FRAMES": "24"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "obs/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("obs/s residual+Jacobian+Schur") and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert "workload" in d["config"] and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["converge"]["status"] > 0 and cb["converge"]["wall_s"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_engine_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = _run_bench("--steps", "1", "--warmup", "0")
+    assert out.returncode != 0
+    assert "no CPU fallback" in out.stderr and not out.stdout.strip()
