@@ -9,14 +9,13 @@ Schur kernels; the finite-difference sparsity pattern is never
 built on that path.
 """
 import ctypes
-import warnings
 
 import numpy as np
 
 from . import _native
 from ._native import check
 from .engine import BAProblem
-from .geometry import project_points, project_points_multi
+from .geometry import project_points_multi
 
 na = np.newaxis
 
