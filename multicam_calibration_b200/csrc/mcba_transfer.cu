@@ -34,15 +34,20 @@ struct Staging {
   cudaEvent_t ready = nullptr;   // caller's stream -> worker streams
 };
 
+// one staging context per device (streams and events belong to a device): a process that drives
+// several GPUs, or a rank that touched cuda:0 before selecting its own device, stages on each
+constexpr int kMaxDevices = 64;
 std::mutex g_mu;
-Staging g_stage;
+Staging g_stages[kMaxDevices];
 
-int ensure_staging(int device) {
-  if (g_stage.device == device) return MCBA_OK;
-  if (g_stage.device >= 0) {
-    set_error("mcba_upload/mcba_download: staging buffers are bound to another device");
-    return MCBA_ERR_STATE;
+int ensure_staging(int device, Staging** out) {
+  if (device < 0 || device >= kMaxDevices) {
+    set_error("mcba_upload/mcba_download: device index out of range");
+    return MCBA_ERR_ARG;
   }
+  Staging& g_stage = g_stages[device];
+  *out = &g_stage;
+  if (g_stage.device == device) return MCBA_OK;
   for (Lane& l : g_stage.lanes) {
     for (int b = 0; b < 2; ++b) {
       MCBA_CUDA(cudaHostAlloc((void**)&l.buf[b], kChunk, cudaHostAllocDefault));
@@ -75,8 +80,10 @@ int staged_copy(int device, cudaStream_t stream, unsigned char* dev, unsigned ch
     MCBA_CUDA(cudaStreamSynchronize(stream));
     return MCBA_OK;
   }
-  int rc = ensure_staging(device);
+  Staging* stage_ptr = nullptr;
+  int rc = ensure_staging(device, &stage_ptr);
   if (rc) return rc;
+  Staging& g_stage = *stage_ptr;
   // everything queued on the caller's stream (the producer of a download, the previous user of an
   // upload target) precedes the worker streams
   MCBA_CUDA(cudaEventRecord(g_stage.ready, stream));

@@ -471,6 +471,43 @@ def analytic_jac_for_scipy(params, all_calib_uvs, calib_objpoints):
                       shape=(m, C * CAM_BLOCK + F * POSE_BLOCK))
 
 
+def sparse_gauss_newton_polish(x, all_calib_uvs, calib_objpoints, fun=None, n_iter=40, lam=1e-8,
+                               gtol=1e-9, trace=None):
+    """Tight minimiser of ``0.5 sum soft_l1(f^2)`` at sizes where a dense Jacobian does not fit
+    (BASELINE configs[0]: 210 000 x 3 072): Gauss-Newton on scipy's Triggs-scaled normal equations
+    (optimize/_lsq/common.py:720-731) assembled sparse from the analytic Jacobian and factored with
+    SuperLU (``scipy.sparse.linalg.splu``); ``lam * diag`` keeps the 6-D rigid gauge
+    non-singular, a step is kept only if it does not raise the cost.  ``fun`` is the residual
+    function (default: the oracle's; the fixture generator passes the reference's).  Returns
+    ``(x, cost, ||g||_inf)`` with ``g = J^T (rho' f)`` the gradient at the returned point."""
+    from scipy.sparse import diags
+    from scipy.sparse.linalg import splu
+    fun = residuals if fun is None else fun
+    x = np.asarray(x, dtype=float).copy()
+    cost_of = lambda p: 0.5 * loss_rho(fun(p, all_calib_uvs, calib_objpoints))[0].sum()
+    cost, stalled = cost_of(x), 0
+    for it in range(n_iter):
+        f = fun(x, all_calib_uvs, calib_objpoints)
+        J = analytic_jac_for_scipy(x, all_calib_uvs, calib_objpoints)
+        _, r1, r2 = loss_rho(f)
+        g = J.T @ (r1 * f)
+        gnorm = float(np.abs(g).max())
+        if trace is not None:
+            trace.append((it, cost, gnorm))
+        if gnorm < gtol or stalled >= 3:
+            break
+        Js = diags(np.sqrt(np.maximum(r1 + 2 * r2 * f ** 2, EPS))) @ J
+        H = (Js.T @ Js).tocsc()
+        step = -splu((H + diags(lam * H.diagonal())).tocsc()).solve(g)
+        cost_new = cost_of(x + step)
+        if cost_new <= cost:
+            x, cost, stalled = x + step, cost_new, (stalled + 1 if cost_new == cost else 0)
+        else:
+            lam *= 10.0
+            stalled += 1
+    return x, cost, gnorm
+
+
 # --------------------------------------------------------------------------
 # initialisation algebra (calibration.py; SURVEY.md 8(f) row N2)
 # --------------------------------------------------------------------------

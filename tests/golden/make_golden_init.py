@@ -2,7 +2,7 @@
 reference ``multicam_calibration.calibration`` (calibration.py:116-277), imported through the
 stub package of make_golden.py.  Build container only (needs /root/reference and networkx):
 
-    python tests/golden/make_golden_init.py
+    python tests/golden/make_golden_init.py [--check]
 
 Also asserts that ``oracle/np_oracle.py`` reproduces the reference on every fixture and that the
 host-side spanning tree of the package (no networkx) orders edges like the reference, ties
@@ -17,7 +17,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from make_golden import close, load_reference   # noqa: E402
+from make_golden import check_fixture, close, load_reference   # noqa: E402
 
 
 def main():
@@ -69,8 +69,11 @@ def main():
     out.update({"R": R, "R_vec": geo.rodrigues_inv(R), "T": T, "T_vec": geo.get_transformation_vector(T)})
     close(out["R_vec"], orc.rodrigues_inv(R), 1e-15, "rodrigues_inv")
     close(out["T_vec"], orc.transformation_vector(T), 1e-15, "get_transformation_vector")
-    np.savez_compressed(os.path.join(HERE, "init.npz"), **out)
-    print("wrote init.npz")
+    if "--check" in sys.argv[1:]:
+        check_fixture("init", out)
+    else:
+        np.savez_compressed(os.path.join(HERE, "init.npz"), **out)
+        print("wrote init.npz")
 
 
 if __name__ == "__main__":
