@@ -191,6 +191,10 @@ extern "C" int mcba_select_frames(int device, void* cuda_stream, const double* d
   MCBA_CUDA(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const long long rows = (long long)C * F, total = rows * N;
+  if (total > 2147483647LL) {   // cub's radix sort takes an int item count
+    set_error("mcba_select_frames: more than 2^31 - 1 (camera, frame, corner) slots in one call; shard the frames");
+    return MCBA_ERR_ARG;
+  }
   // One stream-ordered allocation carved into the work arrays.  The device's default memory pool
   // keeps the block between calls (release threshold raised once), so a repeated call pays no
   // cudaMalloc / cudaFree (those cost ~15 ms here for ~0.3 ms of kernels and a 2 ms sort).
@@ -202,8 +206,9 @@ extern "C" int mcba_select_frames(int device, void* cuda_stream, const double* d
                o_stats = o_mean + up(sizeof(double) * rows), o_cnt = o_stats + 256, o_cams = o_cnt + 256,
                o_complete = o_cams + up(sizeof(CamConst) * C), o_elig = o_complete + up(rows), o_tmp = o_elig + up(F),
                ws_bytes = o_tmp + up(tmp_bytes ? tmp_bytes : 8);
-  unsigned char* ws = nullptr;
-  MCBA_CUDA(cudaMallocAsync((void**)&ws, ws_bytes, st));
+  AsyncBlock block(st);   // released on every return
+  MCBA_CUDA(cudaMallocAsync((void**)&block.p, ws_bytes, st));
+  unsigned char* ws = block.p;
   double* d_err = reinterpret_cast<double*>(ws + o_err);
   double* d_sorted = reinterpret_cast<double*>(ws + o_sorted);
   double* d_mean = reinterpret_cast<double*>(ws + o_mean);
@@ -236,7 +241,6 @@ extern "C" int mcba_select_frames(int device, void* cuda_stream, const double* d
   h_stats[1] = (double)cnt[0];        // eligible frames
   h_stats[2] = (double)excluded;      // excluded as outliers
   h_stats[3] = (double)cnt[1];        // finite error values
-  MCBA_CUDA(cudaFreeAsync(ws, st));
   return MCBA_OK;
 }
 

@@ -1,6 +1,7 @@
 // K2b: S_raw = sum_f Z_f Z_f^T and Z_f y_f (register-tiled SYRK over the frame
 // axis), the finalisation of the packed reduced camera system in the true
-// parameter basis, the damped Cholesky solve and K3, the pose back-substitution.
+// parameter basis and K3, the pose back-substitution (the damped Cholesky solve
+// between the two is k3_solve.cu).
 // Math: SURVEY.md Appendix A ("Schur form for this problem").
 #include <cstdlib>
 
@@ -559,39 +560,6 @@ int launch_finalize(mcba_handle* h) {
   finalize_kernel<<<L.C * L.C + 1, 160, 0, h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
-  return MCBA_OK;
-}
-
-// ------------------------------------------------------------------ damped system
-__global__ void damp_kernel(const double* __restrict__ red, long long offS, long long offB, long long offDiag,
-                            int nc, double lambda, double* __restrict__ D2cam, double* __restrict__ Sd,
-                            double* __restrict__ rhs) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nc * nc) return;
-  const int r = i / nc, q = i % nc;
-  double v = red[offS + i];
-  if (r == q) {
-    double d2 = fmax(D2cam[r], red[offDiag + r]);
-    D2cam[r] = d2;
-    if (d2 == 0.0) d2 = 1.0;
-    v = fma(lambda, d2, v);
-    rhs[r] = -red[offB + r];
-  }
-  Sd[i] = v;
-}
-
-int solve_reduced(mcba_handle* h, double lambda) {
-  const Layout& L = h->L;
-  const int nc = L.nc;
-  damp_kernel<<<(nc * nc + 255) / 256, 256, 0, h->stream>>>(h->d_red, L.offS, L.offB, L.offDiag, nc, lambda,
-                                                            h->d_D2cam, h->d_Sd, h->d_dcam);
-  h->launches++;
-  MCBA_CUDA(cudaGetLastError());
-  cusolverStatus_t st = cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, nc, h->d_Sd, nc, h->d_work, h->lwork, h->d_info);
-  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnDpotrf failed"); return MCBA_ERR_SOLVER; }
-  st = cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, nc, 1, h->d_Sd, nc, h->d_dcam, nc, h->d_info + 1);
-  if (st != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnDpotrs failed"); return MCBA_ERR_SOLVER; }
-  h->launches += 4;  // potrf + potrs kernels (library; approximate count)
   return MCBA_OK;
 }
 

@@ -185,8 +185,9 @@ extern "C" int mcba_pairwise_transform(int device, void* cuda_stream, const doub
   cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const double*)nullptr, (double*)nullptr, (int)F, 0, 64, st);
   auto up = [](size_t b) { return (b + 255) / 256 * 256; };
   const size_t o_keys = 0, o_sorted = up(sizeof(double) * 6 * F), o_small = 2 * o_sorted, o_tmp = o_small + 256;
-  unsigned char* ws = nullptr;
-  MCBA_CUDA(cudaMallocAsync((void**)&ws, o_tmp + up(tmp_bytes ? tmp_bytes : 8), st));
+  AsyncBlock block(st);   // released on every return
+  MCBA_CUDA(cudaMallocAsync((void**)&block.p, o_tmp + up(tmp_bytes ? tmp_bytes : 8), st));
+  unsigned char* ws = block.p;
   double* keys = reinterpret_cast<double*>(ws + o_keys);
   double* sorted = reinterpret_cast<double*>(ws + o_sorted);
   double* d_out = reinterpret_cast<double*>(ws + o_small);
@@ -201,7 +202,6 @@ extern "C" int mcba_pairwise_transform(int device, void* cuda_stream, const doub
   MCBA_CUDA(cudaMemcpyAsync(h_transform, d_out, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
   MCBA_CUDA(cudaMemcpyAsync(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost, st));
   MCBA_CUDA(cudaStreamSynchronize(st));
-  MCBA_CUDA(cudaFreeAsync(ws, st));
   if (h_n_common) *h_n_common = (int64_t)n;
   return MCBA_OK;
 }
@@ -219,9 +219,10 @@ extern "C" int mcba_consensus_poses(int device, void* cuda_stream, const double*
   MCBA_CUDA(cudaSetDevice(device));
   { int rc = keep_async_pool(device); if (rc) return rc; }
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  unsigned char* ws = nullptr;
+  AsyncBlock block(st);   // released on every return
   const size_t ext_bytes = (sizeof(double) * 6 * C + 255) / 256 * 256;
-  MCBA_CUDA(cudaMallocAsync((void**)&ws, ext_bytes + sizeof(ExtConst) * C, st));
+  MCBA_CUDA(cudaMallocAsync((void**)&block.p, ext_bytes + sizeof(ExtConst) * C, st));
+  unsigned char* ws = block.p;
   double* d_ext = reinterpret_cast<double*>(ws);
   ExtConst* d_E = reinterpret_cast<ExtConst*>(ws + ext_bytes);
   MCBA_CUDA(cudaMemcpyAsync(d_ext, h_extrinsics, sizeof(double) * 6 * C, cudaMemcpyHostToDevice, st));
@@ -232,7 +233,6 @@ extern "C" int mcba_consensus_poses(int device, void* cuda_stream, const double*
   else consensus_poses_kernel<32><<<grid, 128, 0, st>>>(d_all_poses, d_E, C, F, d_poses);
   MCBA_CUDA(cudaGetLastError());
   MCBA_CUDA(cudaStreamSynchronize(st));   // h_extrinsics may be a temporary
-  MCBA_CUDA(cudaFreeAsync(ws, st));
   return MCBA_OK;
 }
 

@@ -198,17 +198,9 @@ void mcba_default_options(mcba_options* o) {
   o->lambda_max = 1e12;
 }
 
-int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
-  if (!out || C < 1 || F < 1 || N < 1) {
-    set_error("mcba_create: n_cameras, n_frames, n_points must be >= 1");
-    return MCBA_ERR_ARG;
-  }
-  if (C > 32) {
-    set_error("mcba_create: at most 32 cameras are supported");
-    return MCBA_ERR_ARG;
-  }
+// allocations and library handles of a new problem; on failure the caller destroys the partly built handle
+static int create_impl(mcba_handle* h, int C, int64_t F, int N, int device) {
   MCBA_CUDA(cudaSetDevice(device));
-  mcba_handle* h = new mcba_handle();
   h->device = device;
   Layout& L = h->L;
   L.C = C; L.N = N; L.F = F;
@@ -272,16 +264,29 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
   MCBA_CUDA(cudaMemset(h->d_gpose, 0, sizeof(double) * L.Fpad * 6));
   MCBA_CUDA(cudaMemset(h->d_partSyrk, 0, sizeof(double) * (size_t)h->grid_syrk * L.nc8 * L.nc8));   // lower block triangle is never written
   MCBA_CUDA(cudaMallocHost((void**)&h->h_pinned, sizeof(double) * (L.redLen + 64)));
-  if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) {
-    set_error("cusolverDnCreate failed");
-    return MCBA_ERR_SOLVER;
+  // the reduced system is solved by this library's own kernel (k3_solve.cu); a cuSOLVER handle is
+  // only created if a system wider than 192 (more than 16 cameras) is ever solved
+  return MCBA_OK;
+}
+
+int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
+  if (!out || C < 1 || F < 1 || N < 1) {
+    set_error("mcba_create: n_cameras, n_frames, n_points must be >= 1");
+    return MCBA_ERR_ARG;
   }
-  cusolverDnSetStream(h->solver, h->stream);
-  if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, L.nc, h->d_Sd, L.nc, &h->lwork) != CUSOLVER_STATUS_SUCCESS) {
-    set_error("cusolverDnDpotrf_bufferSize failed");
-    return MCBA_ERR_SOLVER;
+  if (C > 32) {
+    set_error("mcba_create: at most 32 cameras are supported");
+    return MCBA_ERR_ARG;
   }
-  MCBA_ALLOC(h->d_work, h->lwork);
+  *out = nullptr;
+  mcba_handle* h = new mcba_handle();
+  const int rc = create_impl(h, C, F, N, device);
+  if (rc) {   // release whatever was allocated before the failure, keep its message
+    const std::string why = g_error;
+    mcba_destroy(h);
+    set_error(why);
+    return rc;
+  }
   *out = h;
   return MCBA_OK;
 }
@@ -320,7 +325,7 @@ int mcba_set_stream(mcba_handle* h, void* s) {
     MCBA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
   }
-  cusolverDnSetStream(h->solver, h->stream);
+  if (h->solver) cusolverDnSetStream(h->solver, h->stream);
   return MCBA_OK;
 }
 
@@ -453,9 +458,10 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
   std::memset(res, 0, sizeof(*res));
   const long long launches0 = h->launches;
 
-  cudaEvent_t ev0, ev1;
-  MCBA_CUDA(cudaEventCreate(&ev0));
-  MCBA_CUDA(cudaEventCreate(&ev1));
+  EventPair timing;   // destroyed on every return
+  MCBA_CUDA(cudaEventCreate(&timing.a));
+  MCBA_CUDA(cudaEventCreate(&timing.b));
+  const cudaEvent_t ev0 = timing.a, ev1 = timing.b;
   MCBA_CUDA(cudaEventRecord(ev0, h->stream));
 
   double* x = h->d_x;
@@ -479,8 +485,18 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
     set_error("Residuals are not finite in the initial point.");
     return MCBA_ERR_NONFINITE;
   }
-  // total parameter count across ranks decides the default evaluation budget (scipy: 100 n)
+  // The TOTAL parameter count decides the default evaluation budget (scipy: 100 n).  With uneven
+  // shards 6 F differs between ranks, and a rank-local budget would let one rank leave the loop --
+  // and the collective -- before the others: sum the pose counts over the ranks once.
   long long n_total = n_local;
+  if (h->nranks > 1 && opt.max_nfev <= 0) {
+    const double mine = 6.0 * (double)L.F;
+    MCBA_CUDA(cudaMemcpyAsync(h->d_scal + 40, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = allreduce_packed(h, h->d_scal + 40, 1))) return rc;
+    MCBA_CUDA(cudaMemcpyAsync(h->h_pinned + L.redLen, h->d_scal + 40, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    MCBA_CUDA(cudaStreamSynchronize(h->stream));
+    n_total = L.nc + (long long)h->h_pinned[L.redLen];
+  }
   int max_nfev = opt.max_nfev > 0 ? opt.max_nfev : (int)std::min<long long>(100 * n_total, 2000000000LL);
   double cost = ev.cost;
   res->cost0 = cost;
@@ -595,8 +611,6 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
   MCBA_CUDA(cudaEventSynchronize(ev1));
   float ms = 0;
   MCBA_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   res->cost = cost;
   res->optimality = ev.gnorm;
   res->rms = ev.count > 0 ? std::sqrt(ev.sumsq / ev.count) : 0.0;

@@ -128,6 +128,24 @@ void set_error(const std::string& msg);
     }                                                                                     \
   } while (0)
 
+// Scope guards for the error paths: a stream-ordered work block and CUDA events are released on
+// every return.
+struct AsyncBlock {
+  unsigned char* p = nullptr;
+  cudaStream_t st = nullptr;
+  explicit AsyncBlock(cudaStream_t s) : st(s) {}
+  AsyncBlock(const AsyncBlock&) = delete;
+  AsyncBlock& operator=(const AsyncBlock&) = delete;
+  ~AsyncBlock() { if (p) cudaFreeAsync(p, st); }
+};
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() = default;
+  EventPair(const EventPair&) = delete;
+  EventPair& operator=(const EventPair&) = delete;
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
 int keep_async_pool(int device);   // k0_frontend.cu
 int peer_allreduce(mcba_handle* h, double* buf, long long n);   // mcba_peer.cu
 

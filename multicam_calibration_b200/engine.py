@@ -57,8 +57,8 @@ class OptimizeResult(dict):
     def __getattr__(self, name):
         try:
             return self[name]
-        except KeyError:
-            return None
+        except KeyError as e:      # like scipy's OptimizeResult: a typo is an error, hasattr() works
+            raise AttributeError(name) from e
 
     def get(self, name, default=None):
         try:
@@ -87,8 +87,16 @@ def _on_stream(fn):
 
     @functools.wraps(fn)
     def wrapper(self, *a, **k):
-        with self.torch.cuda.device(self.device), self.torch.cuda.stream(self.stream):
-            return fn(self, *a, **k)
+        cuda = self.torch.cuda
+        with cuda.device(self.device):
+            # Work the caller queued on ITS current stream (e.g. the device gather that produced a
+            # tensor argument) must precede ours: the problem's stream is non-blocking and has no
+            # implicit ordering against it.  Captured before the stream switch below.
+            caller = cuda.current_stream(self.device)
+            if caller != self.stream:
+                self.stream.wait_stream(caller)
+            with cuda.stream(self.stream):
+                return fn(self, *a, **k)
     return wrapper
 
 
@@ -233,8 +241,7 @@ class BAProblem:
         if on_device:
             if not uvs.is_cuda or uvs.dtype != self.torch.float64:
                 raise ValueError("device observations must be a float64 CUDA tensor")
-            uvs = uvs.contiguous()
-            self.stream.wait_stream(self.torch.cuda.current_stream(self.device))
+            uvs = uvs.contiguous()     # ordered after its producer by _on_stream
             d_obj = self._dev(self._obj)
             check(self.lib.mcba_set_observations(self._h, _ptr(uvs), _ptr(d_obj), 1))
         else:   # pageable numpy -> device at PCIe rate (mcba_upload), then the device path

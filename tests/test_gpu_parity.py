@@ -462,7 +462,9 @@ def test_result_fun_is_lazy_and_matches_residuals():
     *_, result2 = mcc.bundle_adjust(g["uvs"], ext, intr, g["objpoints"], g["init_poses"], n_frames=None, verbose=0)
     mcc.residuals(result2.x, g["uvs"][:, use] + 1.0, g["objpoints"])
     assert np.abs(result2.fun - r_ref).max() <= 1e-10 * np.abs(r_ref).max()
-    assert result2.missing_field is None
+    with pytest.raises(AttributeError):       # like scipy's OptimizeResult
+        result2.missing_field
+    assert not hasattr(result2, "missing_field") and hasattr(result2, "fun")
 
 
 # ------------------------------------------------------------------ initialisation algebra

@@ -154,7 +154,9 @@ def test_optimize_result_lazy_fields():
     assert set(dict(r)) == {"x", "cost"}
     assert r.fun == [1, 2, 3] and r["fun"] == [1, 2, 3] and calls == [1]
     assert dict.__contains__(r, "fun")
-    assert r.missing is None and r.get("missing", 5) == 5
+    assert r.get("missing", 5) == 5 and not hasattr(r, "missing")
+    with pytest.raises(AttributeError):      # scipy's OptimizeResult raises too: a typo is not None
+        r.missing
     with pytest.raises(KeyError):
         r["missing"]
     t = engine.OptimizeResult(a=1)
