@@ -169,6 +169,26 @@ int mcba_comm_ipc_enable(mcba_handle* h, int enable);
 int mcba_select_frames(int device, void* cuda_stream, const double* d_uvs, int n_cameras,
                        int64_t n_frames, int n_points, const double* d_obj, const double* d_x,
                        double outlier_threshold, uint8_t* d_use, double* h_stats);
+/* The same front end in stages, for frame-sharded (multi-GPU) runs: every rank holds a contiguous
+ * range of F frames (d_x = 12C camera parameters + the 6F poses of ITS frames) and only counters
+ * and 256-bin histograms cross ranks (summed by the host side through torch.distributed).
+ *   mcba_frame_errors    bundle_adjustment.py:266-279 on this rank's frames: d_elig (F bytes),
+ *                        d_err (C,F,N) per-point errors (NaN = not counted), d_mean (C,F) nanmean
+ *                        per camera and frame; h_counts[2] = {eligible frames, finite error values}.
+ *   mcba_key_histogram   one pass of an exact radix selection (for the GLOBAL nanmedian of :281-282):
+ *                        counts, by their next 8 bits, the finite values of d_vals whose leading
+ *                        prefix_bits bits (a multiple of 8, <= 56) equal prefix; d_hist: 256 x uint64
+ *                        (device, overwritten).  Values must be non-negative (error norms are).
+ *   mcba_apply_threshold bundle_adjustment.py:279-285 with the (global) threshold: d_use (F bytes),
+ *                        *h_excluded = eligible frames of this rank excluded as outliers. */
+int mcba_frame_errors(int device, void* cuda_stream, const double* d_uvs, int n_cameras,
+                      int64_t n_frames, int n_points, const double* d_obj, const double* d_x,
+                      double* d_err, double* d_mean, uint8_t* d_elig, int64_t* h_counts);
+int mcba_key_histogram(int device, void* cuda_stream, const double* d_vals, int64_t n,
+                       uint64_t prefix, int prefix_bits, uint64_t* d_hist);
+int mcba_apply_threshold(int device, void* cuda_stream, const double* d_mean, const uint8_t* d_elig,
+                         int n_cameras, int64_t n_frames, double threshold, uint8_t* d_use,
+                         int64_t* h_excluded);
 /* all_calib_uvs[:, use_frames] (bundle_adjustment.py:299-312) on the device:
  * d_out (C, n_used, N, 2) = d_uvs (C, F, N, 2)[:, d_idx]. */
 int mcba_gather_frames(int device, void* cuda_stream, const double* d_uvs, int n_cameras,

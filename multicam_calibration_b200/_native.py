@@ -80,6 +80,9 @@ _SIGNATURES = {
     "mcba_profile": (_I, [_P, _I, ctypes.POINTER(_D), ctypes.POINTER(_I)]),
     "mcba_measure_fp64_peak": (_I, [_I, ctypes.POINTER(_D)]),
     "mcba_select_frames": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _D, _P, ctypes.POINTER(_D)]),
+    "mcba_frame_errors": (_I, [_I, _P, _P, _I, _L, _I, _P, _P, _P, _P, _P, ctypes.POINTER(_L)]),
+    "mcba_key_histogram": (_I, [_I, _P, _P, _L, ctypes.c_uint64, _I, _P]),
+    "mcba_apply_threshold": (_I, [_I, _P, _P, _P, _I, _L, _D, _P, ctypes.POINTER(_L)]),
     "mcba_gather_frames": (_I, [_I, _P, _P, _I, _L, _I, _P, _L, _P]),
     "mcba_pairwise_transform": (_I, [_I, _P, _P, _P, _L, ctypes.POINTER(_D), ctypes.POINTER(_L)]),
     "mcba_consensus_poses": (_I, [_I, _P, _P, _P, _I, _L, _P]),
@@ -150,6 +153,20 @@ def to_device(array, device=None):
     check(load().mcba_upload(dev, stream, ctypes.c_void_p(out.data_ptr()), a.ctypes.data_as(ctypes.c_void_p),
                              a.nbytes))
     return out
+
+
+def upload_into(dst, array):
+    """float64 numpy array -> an existing contiguous CUDA tensor (view) of the same size, through
+    ``mcba_upload``; ordered on torch's current stream of the tensor's device."""
+    import numpy as np
+    torch = require_cuda()
+    a = np.ascontiguousarray(array, dtype=np.float64)
+    if not dst.is_contiguous() or dst.dtype != torch.float64 or dst.numel() != a.size:
+        raise ValueError("upload_into: destination must be a contiguous float64 CUDA tensor of the source's size")
+    dev = dst.device.index
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(load().mcba_upload(dev, stream, ctypes.c_void_p(dst.data_ptr()), a.ctypes.data_as(ctypes.c_void_p), a.nbytes))
+    return dst
 
 
 def to_host(tensor):

@@ -149,6 +149,80 @@ def _select_frames_device(all_calib_uvs, all_extrinsics, all_intrinsics, calib_o
     return use_frames, d_uvs
 
 
+def _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
+                           n_frames, outlier_threshold):
+    """The same front end with the frames sharded over the ranks of ``torch.distributed``'s default
+    group (every rank is called with the same, full host arrays, like the reference's call under
+    torchrun).  Rank r uploads and scans only its contiguous range of ALL frames; the nanmedian of
+    :281-282 is found exactly over all ranks by radix selection (256-bin histograms are the only
+    thing summed across ranks); rank 0 draws the random sub-sample of :293-296 and broadcasts it, so
+    every rank sees the same ``use_frames`` whatever its RNG state.
+
+    Returns ``(use_frames, d_uvs_local)``: the kept frames (global indices, identical on all ranks)
+    and THIS rank's share of their observations on its device -- the kept frames of its own range
+    when all are used (nothing is re-uploaded), a balanced slice of the drawn sample otherwise."""
+    from . import distributed
+    torch = _native.require_cuda()
+    lib = _native.load()
+    W, r = distributed.world_size(), distributed.rank()
+    dev = distributed.local_device()
+    torch.cuda.set_device(dev)
+    uvs = np.asarray(all_calib_uvs, dtype=np.float64)
+    C, F, N, _ = uvs.shape
+    if F < W:
+        raise ValueError(f"{F} frames cannot be sharded over {W} ranks")
+    a, b = distributed.shard_bounds(F, W, r)
+    Fl = b - a
+    device = f"cuda:{dev}"
+    d_uvs = torch.empty((C, Fl, N, 2), dtype=torch.float64, device=device)
+    for c in range(C):                                   # uvs[c, a:b] is contiguous: no host-side copy of the shard
+        _native.upload_into(d_uvs[c], uvs[c, a:b])
+    x_loc = serialize_params(all_extrinsics, all_intrinsics, np.asarray(calib_poses, dtype=np.float64)[a:b])
+    d_x, d_obj = _native.to_device(x_loc, dev), _native.to_device(calib_objpoints, dev)
+    d_err = torch.empty((C, Fl, N), dtype=torch.float64, device=device)
+    d_mean = torch.empty((C, Fl), dtype=torch.float64, device=device)
+    d_elig = torch.empty(Fl, dtype=torch.uint8, device=device)
+    d_use = torch.empty(Fl, dtype=torch.uint8, device=device)
+    d_hist = torch.empty(256, dtype=torch.int64, device=device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    counts = (ctypes.c_int64 * 2)()
+    check(lib.mcba_frame_errors(dev, stream, ptr(d_uvs), C, Fl, N, ptr(d_obj), ptr(d_x), ptr(d_err), ptr(d_mean),
+                                ptr(d_elig), counts))
+    n_eligible, n_finite = (int(v) for v in distributed.allreduce_sum(np.array([counts[0], counts[1]], dtype=np.int64)))
+    if outlier_threshold is None:
+        def local_histogram(prefix, prefix_bits):
+            check(lib.mcba_key_histogram(dev, stream, ptr(d_err), d_err.numel(), ctypes.c_uint64(prefix), prefix_bits,
+                                         ptr(d_hist)))
+            return d_hist.cpu().numpy()
+        threshold = 5.0 * distributed.global_nanmedian(local_histogram, n_finite)
+    else:
+        threshold = outlier_threshold
+    excluded = ctypes.c_int64()
+    check(lib.mcba_apply_threshold(dev, stream, ptr(d_mean), ptr(d_elig), C, Fl, float(threshold), ptr(d_use),
+                                   ctypes.byref(excluded)))
+    use_local = torch.nonzero(d_use).ravel()
+    n_excluded = int(distributed.allreduce_sum(np.array([excluded.value], dtype=np.int64))[0])
+    use_frames = np.concatenate(distributed.gather_arrays(use_local.cpu().numpy().astype(np.int64) + a))
+    if r == 0:
+        print(f"Excluding {n_excluded} out of {len(use_frames)} frames "
+              f"based on an outlier threshold of {threshold}")
+    if n_frames is None or n_frames > len(use_frames):
+        out = torch.empty((C, int(use_local.numel()), N, 2), dtype=torch.float64, device=device)
+        if use_local.numel():
+            check(lib.mcba_gather_frames(dev, stream, ptr(d_uvs), C, Fl, N, ptr(use_local), int(use_local.numel()), ptr(out)))
+        return use_frames, out
+    # random sub-sample (bundle_adjustment.py:293-296): drawn once, on rank 0, from ITS global numpy RNG
+    chosen = np.random.choice(use_frames, n_frames, replace=False) if r == 0 else None
+    chosen = distributed.broadcast_object(chosen)
+    lo, hi = distributed.shard_bounds(len(chosen), W, r)
+    mine = chosen[lo:hi]
+    out = torch.empty((C, len(mine), N, 2), dtype=torch.float64, device=device)
+    if len(mine):
+        _native.upload_into(out, uvs[:, mine])          # a shard of the (small) sample from the caller's array
+    return chosen, out
+
+
 def select_frames(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
                   n_frames=10000, outlier_threshold=None):
     """Frame eligibility, outlier rejection and sub-sampling of
@@ -189,13 +263,20 @@ def bundle_adjust(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints
     calib_poses = np.asarray(calib_poses, dtype=np.float64)
     calib_objpoints = np.asarray(calib_objpoints, dtype=np.float64)
     n_cameras = all_calib_uvs.shape[0]
-    use_frames, d_uvs = _select_frames_device(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
-                                              calib_poses, n_frames, outlier_threshold)
-    x0 = serialize_params(all_extrinsics, all_intrinsics, calib_poses[use_frames])
     if distributed.world_size() > 1:
-        del d_uvs
-        x, result = distributed.solve_sharded(all_calib_uvs[:, use_frames], calib_objpoints, x0, **opt_kwargs)
+        # every rank uploads, scans and solves only its own frames; use_frames is rank-contiguous
+        use_frames, d_local = _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
+                                                     calib_poses, n_frames, outlier_threshold)
+        counts = distributed.allreduce_sum(np.eye(distributed.world_size(), dtype=np.int64)[distributed.rank()]
+                                           * int(d_local.shape[1]))
+        lo = int(counts[:distributed.rank()].sum())
+        x0_local = serialize_params(all_extrinsics, all_intrinsics, calib_poses[use_frames[lo:lo + int(d_local.shape[1])]])
+        x, result = distributed.solve_sharded(d_local, calib_objpoints, x0_local, **opt_kwargs)
+        del d_local
     else:
+        use_frames, d_uvs = _select_frames_device(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
+                                                  calib_poses, n_frames, outlier_threshold)
+        x0 = serialize_params(all_extrinsics, all_intrinsics, calib_poses[use_frames])
         prob = _problem_for(_gather_frames_device(d_uvs, use_frames), calib_objpoints)
         del d_uvs
         x, result = prob.solve(x0, **opt_kwargs)

@@ -162,6 +162,28 @@ __global__ void gather_frames_kernel(const double2* __restrict__ src, int C, lon
   }
 }
 
+// Histogram of the next 8 key bits of the finite, non-negative values whose leading `prefix_bits`
+// bits equal `prefix` (IEEE-754 bit patterns of non-negative doubles order like the values): one
+// pass of an exact most-significant-digit radix selection.  Frame-sharded runs find the global
+// nanmedian of the per-point errors with eight such passes and one 256-counter sum across ranks
+// each, instead of gathering the error arrays.
+__global__ void key_histogram_kernel(const double* __restrict__ vals, long long n, unsigned long long prefix,
+                                     int prefix_bits, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int s_hist[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int shift = 64 - prefix_bits - 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = vals[i];
+    if (!(v == v)) continue;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+    if (prefix_bits == 0 || (key >> (64 - prefix_bits)) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xffull], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+
 // The device's default stream-ordered memory pool keeps freed blocks (release threshold raised
 // once per device), so the work arrays of the one-shot entry points cost no cudaMalloc / cudaFree
 // after their first call.
@@ -241,6 +263,84 @@ extern "C" int mcba_select_frames(int device, void* cuda_stream, const double* d
   h_stats[1] = (double)cnt[0];        // eligible frames
   h_stats[2] = (double)excluded;      // excluded as outliers
   h_stats[3] = (double)cnt[1];        // finite error values
+  return MCBA_OK;
+}
+
+// ---- the same front end in stages, for frame-sharded (multi-GPU) runs: every rank calls these on
+// its own contiguous range of frames and only counters / histograms cross ranks
+extern "C" int mcba_frame_errors(int device, void* cuda_stream, const double* d_uvs, int C, int64_t F, int N,
+                                 const double* d_obj, const double* d_x, double* d_err, double* d_mean,
+                                 uint8_t* d_elig, int64_t* h_counts) {
+  if (!d_uvs || !d_obj || !d_x || !d_err || !d_mean || !d_elig || !h_counts || C < 1 || F < 1 || N < 1) {
+    set_error("mcba_frame_errors: bad arguments");
+    return MCBA_ERR_ARG;
+  }
+  MCBA_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  { int rc = keep_async_pool(device); if (rc) return rc; }
+  const long long rows = (long long)C * F;
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_cnt = 0, o_cams = 256, o_complete = o_cams + up(sizeof(CamConst) * C), ws_bytes = o_complete + up(rows);
+  AsyncBlock block(st);
+  MCBA_CUDA(cudaMallocAsync((void**)&block.p, ws_bytes, st));
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(block.p + o_cnt);
+  CamConst* d_cams = reinterpret_cast<CamConst*>(block.p + o_cams);
+  unsigned char* d_complete = block.p + o_complete;
+  MCBA_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 2, st));
+  const int blocks = 148 * 8;
+  prep_cameras_frontend_kernel<<<(C + 31) / 32, 32, 0, st>>>(d_x, C, d_cams);
+  complete_rows_kernel<<<blocks, 256, 0, st>>>(d_uvs, rows, N, d_complete);
+  eligible_kernel<<<(int)((F + 255) / 256), 256, 0, st>>>(d_complete, C, F, d_elig, d_cnt);
+  frame_errors_kernel<<<blocks, 256, 0, st>>>(d_uvs, d_obj, d_x, d_cams, d_elig, C, F, N, d_err, d_mean, d_cnt + 1);
+  MCBA_CUDA(cudaGetLastError());
+  unsigned long long cnt[2];
+  MCBA_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  MCBA_CUDA(cudaStreamSynchronize(st));
+  h_counts[0] = (int64_t)cnt[0];   // eligible frames
+  h_counts[1] = (int64_t)cnt[1];   // finite error values
+  return MCBA_OK;
+}
+
+extern "C" int mcba_key_histogram(int device, void* cuda_stream, const double* d_vals, int64_t n, uint64_t prefix,
+                                  int prefix_bits, uint64_t* d_hist) {
+  if (!d_vals || !d_hist || n < 0 || prefix_bits < 0 || prefix_bits > 56 || prefix_bits % 8) {
+    set_error("mcba_key_histogram: bad arguments");
+    return MCBA_ERR_ARG;
+  }
+  MCBA_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  MCBA_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(uint64_t) * 256, st));
+  if (n == 0) return MCBA_OK;
+  const long long want = (n + 1023) / 1024;
+  const int grid = (int)(want < 148 * 8 ? want : 148 * 8);
+  key_histogram_kernel<<<grid, 256, 0, st>>>(d_vals, n, (unsigned long long)prefix, prefix_bits,
+                                             reinterpret_cast<unsigned long long*>(d_hist));
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
+}
+
+extern "C" int mcba_apply_threshold(int device, void* cuda_stream, const double* d_mean, const uint8_t* d_elig, int C,
+                                    int64_t F, double threshold, uint8_t* d_use, int64_t* h_excluded) {
+  if (!d_mean || !d_elig || !d_use || !h_excluded || C < 1 || F < 1) {
+    set_error("mcba_apply_threshold: bad arguments");
+    return MCBA_ERR_ARG;
+  }
+  MCBA_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  { int rc = keep_async_pool(device); if (rc) return rc; }
+  AsyncBlock block(st);
+  MCBA_CUDA(cudaMallocAsync((void**)&block.p, 256, st));
+  double* d_stats = reinterpret_cast<double*>(block.p);                              // [threshold, excluded]
+  unsigned long long* d_zero = reinterpret_cast<unsigned long long*>(block.p + 64);   // "no finite values": a NaN threshold stays NaN
+  MCBA_CUDA(cudaMemsetAsync(block.p, 0, 256, st));
+  select_kernel<<<(int)((F + 255) / 256), 256, 0, st>>>(nullptr, d_zero, d_mean, d_elig, C, F, threshold, d_use, d_stats);
+  MCBA_CUDA(cudaGetLastError());
+  double stats[2];
+  MCBA_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+  MCBA_CUDA(cudaStreamSynchronize(st));
+  unsigned long long excluded;
+  memcpy(&excluded, &stats[1], sizeof(excluded));
+  *h_excluded = (int64_t)excluded;
   return MCBA_OK;
 }
 

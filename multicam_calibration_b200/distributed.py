@@ -4,10 +4,15 @@ One process per GPU (``torchrun``).  Frames are independent given the camera
 parameters, so each rank owns a contiguous range of frames, runs the fused
 residual/Jacobian/Schur kernels on its range, and only the packed reduced camera
 system ``[S | b | g | diag | scalars]`` (5.4k doubles at 6 cameras) is summed
-with one NCCL all-reduce per evaluation inside ``libmcba``.  Every rank solves
-the small system redundantly (identical inputs, so no broadcast) and
-back-substitutes its own poses.  ``torch.distributed`` provides the rendezvous:
-the ncclUniqueId broadcast and the final gather of poses.
+once per evaluation inside ``libmcba`` (one kernel over NVLink peer memory, or
+NCCL).  Every rank solves the small system redundantly (identical inputs, so no
+broadcast) and back-substitutes its own poses.  The front end of ``bundle_adjust``
+(bundle_adjustment.py:265-296) is sharded the same way: every rank uploads and
+scans only ITS frames, the global nanmedian of the per-point errors is found by an
+exact radix selection whose 256-bin histograms are the only thing summed across
+ranks, and rank 0 draws the random sub-sample for everybody.  ``torch.distributed``
+provides the rendezvous and those small sums; the data path has no collective
+other than the reduced-system sum.
 """
 import os
 
@@ -71,41 +76,137 @@ def broadcast_unique_id():
 
 def gather_arrays(local):
     """All ranks receive the list of every rank's array (host objects; poses are small)."""
+    if world_size() == 1:
+        return [np.asarray(local)]
     dist = _dist()
     out = [None] * world_size()
     dist.all_gather_object(out, np.asarray(local))
     return out
 
 
-def solve_sharded(uvs_used, calib_objpoints, x0, **opt_kwargs):
+def allreduce_sum(values):
+    """Element-wise sum over ranks of a small host array (int64 / float64); every rank gets the
+    result.  NCCL groups carry it in a device tensor, gloo groups (CPU tests) in a host tensor."""
+    import torch
+    dist = _dist()
+    a = np.ascontiguousarray(values)
+    if world_size() == 1:
+        return a.copy()
+    t = torch.from_numpy(a.copy())
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t)
+    return t.cpu().numpy()
+
+
+def broadcast_object(obj, src=0):
+    dist = _dist()
+    if world_size() == 1:
+        return obj
+    box = [obj if rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def kth_smallest(local_histogram, ks, reduce=allreduce_sum):
+    """Exact ``k``-th smallest (0-based, one per entry of ``ks``) of the union over ranks of
+    non-negative float64 values, by most-significant-digit radix selection on the IEEE-754 bit
+    patterns: eight passes of 8 bits; per pass every rank histograms ITS values under the
+    current prefixes (``local_histogram(prefix, prefix_bits) -> 256 int64 counts``) and the counts
+    are summed over ranks.  Nothing but 256-entry histograms crosses ranks."""
+    state = [(0, int(k)) for k in ks]          # (prefix, rank of the wanted value among the values under the prefix)
+    for p in range(8):
+        prefixes = sorted({pre for pre, _ in state})
+        local = np.stack([np.asarray(local_histogram(pre, 8 * p), dtype=np.int64) for pre in prefixes])
+        total = reduce(local)
+        nxt = []
+        for pre, k in state:
+            cum = np.cumsum(total[prefixes.index(pre)])
+            b = int(np.searchsorted(cum, k, side="right"))
+            if b > 255:
+                raise ValueError("kth_smallest: k is not smaller than the number of values")
+            nxt.append(((pre << 8) | b, k - (int(cum[b - 1]) if b else 0)))
+        state = nxt
+    return [float(np.array([pre], dtype=np.uint64).view(np.float64)[0]) for pre, _ in state]
+
+
+def global_nanmedian(local_histogram, n_finite_total, reduce=allreduce_sum):
+    """``np.nanmedian`` of the union over ranks (mean of the two middle values for an even count)."""
+    n = int(n_finite_total)
+    if n == 0:
+        return float("nan")
+    if n & 1:
+        return kth_smallest(local_histogram, [n // 2], reduce)[0]
+    lo, hi = kth_smallest(local_histogram, [n // 2 - 1, n // 2], reduce)
+    return 0.5 * (lo + hi)
+
+
+def gather_device_vectors(local):
+    """Concatenation inputs for a per-rank device vector: returns the list of every rank's vector
+    (device tensors on NCCL groups: one padded ``all_gather_into_tensor`` over NVLink)."""
+    import torch
+    dist = _dist()
+    W = world_size()
+    n = allreduce_sum(np.eye(W, dtype=np.int64)[rank()] * int(local.numel()))
+    if dist.get_backend() != "nccl":
+        out = [None] * W
+        dist.all_gather_object(out, local.cpu().numpy())
+        return [torch.from_numpy(o) for o in out]
+    cap = int(n.max())
+    mine = torch.zeros(cap, dtype=local.dtype, device=local.device)
+    mine[:local.numel()] = local
+    full = torch.empty(W * cap, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, mine)
+    return [full[r * cap: r * cap + int(n[r])] for r in range(W)]
+
+
+def solve_sharded(uvs_local, calib_objpoints, x0_local, **opt_kwargs):
     """Solve with frames sharded over the ranks of the default process group.
 
-    ``uvs_used`` (C,F,N,2) and ``x0`` are the full (replicated) problem; the return
-    value ``(x, result)`` is the full solution on every rank.
+    ``uvs_local`` (C,F_r,N,2): THIS rank's frames (numpy array or float64 CUDA tensor);
+    ``x0_local``: the 12C camera parameters (identical on all ranks) followed by the poses of this
+    rank's frames.  Ranks may hold different numbers of frames (at least one each).  Returns
+    ``(x, result)``: the full solution, poses concatenated in rank order, on every rank;
+    ``result.fun`` is the full residual vector in the reference's order
+    (bundle_adjustment.py:97: camera-major, so every camera's block is the concatenation of the
+    ranks' blocks), gathered over NVLink at the end of the solve and copied to the host on first access.
     """
     import torch
     from .engine import BAProblem
     W, r = world_size(), rank()
-    C, F = uvs_used.shape[0], uvs_used.shape[1]
-    if F < W:
-        raise ValueError(f"{F} frames cannot be sharded over {W} ranks")
-    start, stop = shard_bounds(F, W, r)
+    C, F_local = int(uvs_local.shape[0]), int(uvs_local.shape[1])
+    counts = allreduce_sum(np.eye(W, dtype=np.int64)[r] * F_local)
+    if counts.min() < 1:
+        raise ValueError(f"every rank needs at least one frame (frames per rank: {counts.tolist()})")
+    start = int(counts[:r].sum())
     dev = local_device()
     torch.cuda.set_device(dev)
     uid = broadcast_unique_id()
-    prob = BAProblem(uvs_used[:, start:stop], calib_objpoints, device=dev, comm=(uid, r, W))
+    prob = BAProblem(uvs_local, calib_objpoints, device=dev, comm=(uid, r, W))
+    nc = 12 * C
     try:
-        x_loc, result = prob.solve(split_params(x0, C, start, stop), **opt_kwargs)
+        x_loc, result = prob.solve(np.asarray(x0_local, dtype=np.float64), **opt_kwargs)
         result["peer_memory"] = bool(getattr(prob, "peer_memory", False))
+        result["collective"] = "peer" if result["peer_memory"] else "nccl"
+        # residuals at the solution: computed by every rank on its frames, gathered on the device
+        d_r, per_cam = prob.residuals_device(x_loc)
+        parts = gather_device_vectors(d_r)
+        per_cam_all = allreduce_sum(np.eye(W, dtype=np.int64)[r][:, None] * per_cam[None, :])   # (W, C)
     finally:
         prob.close()
-    nc = 12 * C
     poses = gather_arrays(x_loc[nc:])
     grads = gather_arrays(result.grad[nc:])
     x = merge_params(x_loc[:nc], poses)
     result["x"] = x
     result["grad"] = merge_params(result.grad[:nc], grads)
     result["active_mask"] = np.zeros_like(x)
-    result["fun"] = None   # the residual vector interleaves ranks per camera; not gathered
-    result["shard"] = (start, stop)
+    result["shard"] = (start, start + F_local)
+
+    def fun():
+        offs = np.concatenate([np.zeros((W, 1), dtype=np.int64), np.cumsum(per_cam_all, axis=1)], axis=1)
+        pieces = [parts[q][int(offs[q, c]): int(offs[q, c + 1])] for c in range(C) for q in range(W)]
+        full = torch.cat(pieces) if pieces else parts[0][:0]
+        from . import _native
+        return _native.to_host(full) if full.is_cuda else full.numpy()
+    result.set_lazy("fun", fun)
     return x, result

@@ -241,12 +241,13 @@ class BAProblem:
         if on_device:
             if not uvs.is_cuda or uvs.dtype != self.torch.float64:
                 raise ValueError("device observations must be a float64 CUDA tensor")
-            uvs = uvs.contiguous()     # ordered after its producer by _on_stream
+            d_uvs = uvs.contiguous()     # ordered after its producer by _on_stream
             d_obj = self._dev(self._obj)
-            check(self.lib.mcba_set_observations(self._h, _ptr(uvs), _ptr(d_obj), 1))
         else:   # pageable numpy -> device at PCIe rate (mcba_upload), then the device path
             d_uvs, d_obj = self._dev(uvs), self._dev(self._obj)
-            check(self.lib.mcba_set_observations(self._h, _ptr(d_uvs), _ptr(d_obj), 1))
+        check(self.lib.mcba_set_observations(self._h, _ptr(d_uvs), _ptr(d_obj), 1))
+        if self.world > 1:   # finite scalars per camera: where this rank's residuals go in the gathered vector
+            self._per_camera = self.torch.isfinite(d_uvs).sum(dim=(1, 2, 3)).cpu().numpy().astype(np.int64)
         check(self.lib.mcba_synchronize(self._h))   # uvs may be a temporary
         self._obs_token = object()
 
@@ -274,6 +275,17 @@ class BAProblem:
         r = self._empty(self.n_residuals)
         check(self.lib.mcba_residuals(self._h, _ptr(x), _ptr(r)))
         return _native.to_host(r)
+
+    @_on_stream
+    def residuals_device(self, params):
+        """Residual vector left on the device + the number of entries per camera (the vector is
+        camera-major, bundle_adjustment.py:97) -- what a frame-sharded solve gathers."""
+        x = self._x(params)
+        r = self._empty(self.n_residuals)
+        check(self.lib.mcba_residuals(self._h, _ptr(x), _ptr(r)))
+        check(self.lib.mcba_synchronize(self._h))
+        per_cam = getattr(self, "_per_camera", None)
+        return r, per_cam
 
     @_on_stream
     def predict(self, params):

@@ -415,6 +415,107 @@ def test_select_frames_device_matches_oracle(threshold, capsys):
         assert float(msg[-1]) == pytest.approx(float(thr_o), rel=1e-12)
 
 
+def test_sharded_front_end_equals_the_single_device_front_end(capsys):
+    """The staged front end of frame-sharded runs (mcba_frame_errors + radix-selection median through
+    mcba_key_histogram + mcba_apply_threshold; one rank here) keeps exactly the frames, prints exactly
+    the threshold and consumes the RNG exactly like the single-device front end and the oracle."""
+    import torch
+    from multicam_calibration_b200 import bundle_adjustment as ba
+    sc = make_scene(5, 211, sigma=0.4, p_missing_view=0.35, p_missing_corner=0.03, seed=17)
+    uvs = sc.uvs.copy()
+    rng = np.random.default_rng(3)
+    bad = rng.choice(211, 12, replace=False)
+    uvs[:, bad] += rng.normal(0, 40.0, uvs[:, bad].shape)
+    _, ext, intr, obj, poses = sc.init_args()
+    for nf, thr in ((None, None), (40, None), (None, 2.5)):
+        np.random.seed(1)
+        use_a = mcc.select_frames(uvs, ext, intr, obj, poses, n_frames=nf, outlier_threshold=thr)
+        msg_a = capsys.readouterr().out.strip().splitlines()[0]
+        np.random.seed(1)
+        use_b, d_local = ba._select_frames_sharded(uvs, ext, intr, obj, poses, nf, thr)
+        msg_b = capsys.readouterr().out.strip().splitlines()[0]
+        assert np.array_equal(use_a, use_b) and msg_a == msg_b
+        assert np.array_equal(d_local.cpu().numpy(), uvs[:, use_b], equal_nan=True)
+    # the histogram kernel against numpy on the raw bit patterns
+    import ctypes
+    from multicam_calibration_b200 import _native
+    vals = np.abs(rng.normal(0, 3, 100003))
+    vals[::5] = np.nan
+    vals[7] = 0.0
+    d_vals = _native.to_device(vals)
+    d_hist = torch.empty(256, dtype=torch.int64, device="cuda")
+    keys = vals[~np.isnan(vals)].view(np.uint64)
+    top = int(np.bincount((keys >> np.uint64(56)).astype(np.int64)).argmax())
+    for prefix, bits in ((0, 0), (top, 8)):
+        _native.check(_native.load().mcba_key_histogram(torch.cuda.current_device(), ctypes.c_void_p(
+            torch.cuda.current_stream().cuda_stream), ctypes.c_void_p(d_vals.data_ptr()), vals.size,
+            ctypes.c_uint64(prefix), bits, ctypes.c_void_p(d_hist.data_ptr())))
+        k = keys if bits == 0 else keys[(keys >> np.uint64(64 - bits)) == np.uint64(prefix)]
+        ref = np.bincount(((k >> np.uint64(64 - bits - 8)) & np.uint64(0xff)).astype(np.int64), minlength=256)
+        assert np.array_equal(d_hist.cpu().numpy(), ref)
+
+
+def test_repeated_bundle_adjust_on_the_cached_problem_orders_gather_before_solve():
+    """Two calls of the same shape at a size where the device gather of the kept frames outlasts the
+    host: the second call reuses the cached problem (no allocation in between), so the solve must be
+    ordered after the gather kernel on the caller's stream (the problem runs on its own stream)."""
+    sc = make_scene(6, 20000, sigma=0.5, p_missing_view=0.2, seed=3)
+    args = sc.init_args()
+    outs = []
+    for _ in range(2):
+        np.random.seed(0)
+        e, i, p, use, res = mcc.bundle_adjust(*args, n_frames=None, verbose=0)
+        outs.append((use, res.x, res.cost, res.nfev))
+    x0 = mcc.serialize_params(args[1], args[2], args[4][outs[0][0]])
+    x, r = mcc.BAProblem(args[0][:, outs[0][0]], sc.objpoints).solve(x0, verbose=0)      # host-array path
+    for use, xs, cost, nfev in outs:
+        assert np.array_equal(use, outs[0][0]) and nfev == r.nfev
+        assert cost == pytest.approx(r.cost, rel=1e-12) and np.allclose(xs, x, rtol=0, atol=1e-9)
+    mcc.release_device_memory()
+
+
+def test_handwritten_reduced_solve_matches_the_library_path():
+    """The one-CTA shared-memory Cholesky (k3_solve.cu) against cuSOLVER potrf/potrs on the same
+    damped systems (MCBA_CUSOLVER=1 in a child process), 6 / 9 / 16 cameras; and a non-positive
+    pivot is reported, not propagated silently."""
+    import subprocess
+    import sys
+    import json
+    from conftest import ROOT
+    code = (
+        "import sys, json, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "import multicam_calibration_b200 as mcc\n"
+        "from multicam_calibration_b200.synthetic import make_scene\n"
+        "out = {}\n"
+        "for C, F in ((6, 64), (9, 37), (16, 33)):\n"
+        "    sc = make_scene(C, F, sigma=0.4, p_missing_view=0.3, seed=C)\n"
+        "    prob = mcc.BAProblem(sc.uvs, sc.objpoints)\n"
+        "    prob.build_reduced(sc.x0(), lam=1e-3)\n"
+        "    out[str(C)] = prob.solve_step(1e-3).tolist()\n"
+        "print(json.dumps(out))\n" % ROOT)
+    import os
+    steps = {}
+    for tag, env in (("own", {}), ("lib", {"MCBA_CUSOLVER": "1"})):
+        e = dict(os.environ)
+        e.update(env)
+        run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=e)
+        assert run.returncode == 0, run.stderr[-2000:]
+        steps[tag] = json.loads(run.stdout.strip().splitlines()[-1])
+    for C in ("6", "9", "16"):
+        a, b = np.array(steps["own"][C]), np.array(steps["lib"][C])
+        assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max(), C
+    # lambda = 0: the undamped reduced system is singular along the rigid gauge -> rejected loudly
+    sc = make_scene(3, 12, sigma=0.2, seed=4)
+    prob = mcc.BAProblem(sc.uvs, sc.objpoints)
+    prob.build_reduced(sc.x0(), lam=0.0)
+    try:
+        x1 = prob.solve_step(0.0)
+        assert np.isfinite(x1).all()          # rounding can leave the tiny pivots positive
+    except Exception as err:
+        assert "not positive definite" in str(err)
+
+
 def test_bundle_adjust_device_gather_equals_host_slicing():
     """bundle_adjust (device front end + device gather of the kept frames) ends where a BAProblem
     built from the host-sliced observations ends."""

@@ -100,6 +100,45 @@ def test_shard_bounds_partition_frames():
     assert np.array_equal(distributed.merge_params(parts[0][:24], [p[24:] for p in parts]), x)
 
 
+def _np_histogrammer(vals):
+    """numpy restatement of mcba_key_histogram (csrc/k0_frontend.cu) for one rank's values."""
+    keys = np.ascontiguousarray(vals[~np.isnan(vals)]).view(np.uint64)
+
+    def hist(prefix, bits):
+        k = keys if bits == 0 else keys[(keys >> np.uint64(64 - bits)) == np.uint64(prefix)]
+        return np.bincount(((k >> np.uint64(64 - bits - 8)) & np.uint64(0xff)).astype(np.int64), minlength=256)
+    return hist
+
+
+def test_radix_selection_gives_the_exact_global_nanmedian():
+    """distributed.global_nanmedian (the sharded front end's replacement for np.nanmedian over all
+    ranks' per-point errors, bundle_adjustment.py:281-282) is exact: odd / even counts, ties, zeros,
+    subnormals, NaNs, one rank without any finite value."""
+    rng = np.random.default_rng(0)
+    for n, shards in ((1, 1), (2, 2), (1001, 3), (4096, 4), (20000, 8)):
+        vals = np.abs(rng.normal(0, 3.0, n)) ** rng.integers(1, 4, n)
+        vals[rng.random(n) < 0.2] = np.nan
+        vals[rng.integers(0, n, n // 10)] = vals[0] if vals[0] == vals[0] else 1.5      # ties
+        vals[rng.integers(0, n, 3)] = 0.0
+        vals[rng.integers(0, n, 2)] = 5e-324
+        if np.isnan(vals).all():
+            vals[0] = 2.0
+        parts = np.array_split(vals, shards)
+        if shards > 2:
+            parts[1] = np.full_like(parts[1], np.nan)
+        hists = [_np_histogrammer(p) for p in parts]
+        merged = np.concatenate(parts)
+        local = lambda prefix, bits: np.sum([h(prefix, bits) for h in hists], axis=0)
+        n_finite = int((~np.isnan(merged)).sum())
+        got = distributed.global_nanmedian(local, n_finite, reduce=lambda a: a)
+        assert got == np.nanmedian(merged), (n, shards)
+        ks = sorted({0, n_finite // 3, n_finite - 1})
+        assert distributed.kth_smallest(local, ks, reduce=lambda a: a) == list(np.sort(merged[~np.isnan(merged)])[ks])
+    assert np.isnan(distributed.global_nanmedian(lambda p, b: np.zeros(256, dtype=np.int64), 0, reduce=lambda a: a))
+    with pytest.raises(ValueError):
+        distributed.kth_smallest(_np_histogrammer(np.array([1.0, 2.0])), [2], reduce=lambda a: a)
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -120,6 +159,21 @@ def _gloo_worker(rank, world, port, q):
         dist.all_reduce(packed)
         poses = distributed.gather_arrays(xl[12 * C:])
         x_back = distributed.merge_params(xl[:12 * C], poses)
+        # the small host-side collectives of the sharded front end: counters, the broadcast of rank 0's
+        # random sub-sample (ranks have DIFFERENT RNG states) and the exact global median
+        assert np.array_equal(distributed.allreduce_sum(np.array([rank + 1, 10], dtype=np.int64)), [3, 20])
+        np.random.seed(100 + rank)
+        chosen = distributed.broadcast_object(np.random.choice(50, 7, replace=False) if rank == 0 else None)
+        np.random.seed(100)
+        assert np.array_equal(chosen, np.random.choice(50, 7, replace=False))
+        err = np.abs(np.random.default_rng(3).normal(0, 2, 999))
+        err[::7] = np.nan
+        mine = err[rank::world]
+        med = distributed.global_nanmedian(_np_histogrammer(mine), distributed.allreduce_sum(
+            np.array([(~np.isnan(mine)).sum()], dtype=np.int64))[0])
+        assert med == np.nanmedian(err)
+        vec = distributed.gather_device_vectors(torch.arange(3 + rank, dtype=torch.float64) + 10 * rank)
+        assert [v.tolist() for v in vec] == [[0.0, 1.0, 2.0], [10.0, 11.0, 12.0, 13.0]]
         if rank == 0:
             Hf, gf, cf = orc.normal_equations(x0, uvs, obj)
             Sf, bf = orc.reduced_camera_system(Hf, gf, C)
