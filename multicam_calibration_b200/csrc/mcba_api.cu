@@ -339,9 +339,17 @@ int mcba_set_observations(mcba_handle* h, const double* uvs, const double* obj, 
   if (!h || !uvs || !obj) { set_error("mcba_set_observations: null argument"); return MCBA_ERR_ARG; }
   MCBA_CUDA(cudaSetDevice(h->device));
   const Layout& L = h->L;
-  const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  MCBA_CUDA(cudaMemcpyAsync(h->d_obs_ref, uvs, sizeof(double) * (size_t)L.C * L.F * L.N * 2, kind, h->stream));
-  MCBA_CUDA(cudaMemcpyAsync(h->d_obj, obj, sizeof(double) * 3 * L.N, kind, h->stream));
+  const size_t uv_bytes = sizeof(double) * (size_t)L.C * L.F * L.N * 2;
+  if (is_device) {
+    MCBA_CUDA(cudaMemcpyAsync(h->d_obs_ref, uvs, uv_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    MCBA_CUDA(cudaMemcpyAsync(h->d_obj, obj, sizeof(double) * 3 * L.N, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    // caller-owned host memory: pinned buffers take one async copy, pageable ones (a numpy array) are
+    // staged through the multi-threaded bounce buffers of mcba_upload instead of the driver's single one
+    int rc = mcba_upload(h->device, h->stream, h->d_obs_ref, uvs, uv_bytes);
+    if (rc) return rc;
+    MCBA_CUDA(cudaMemcpyAsync(h->d_obj, obj, sizeof(double) * 3 * L.N, cudaMemcpyHostToDevice, h->stream));
+  }
   int rc = launch_tile_observations(h);
   if (rc) return rc;
   h->have_obs = true;
