@@ -93,10 +93,13 @@ def _problem_for(all_calib_uvs, calib_objpoints):
 
 
 def release_device_memory():
-    """Free the cached device problem (workspaces kept between calls of the same shape)."""
+    """Free the cached device problem (workspaces kept between calls of the same shape) and, in a
+    multi-GPU run, the cached sharded problem with its communicator (call on every rank)."""
     for old in _problems.values():
         old.close()
     _problems.clear()
+    from . import distributed
+    distributed.release_sharded_problem()
 
 
 def residuals(params, all_calib_uvs, calib_objpoints):

@@ -160,6 +160,34 @@ def gather_device_vectors(local):
     return [full[r * cap: r * cap + int(n[r])] for r in range(W)]
 
 
+_sharded = {}
+
+
+def _sharded_problem(uvs_local, calib_objpoints, dev, counts):
+    """The rank's device problem WITH its communicator (NCCL rendezvous + CUDA IPC peer buffers,
+    hundreds of milliseconds to set up) is kept between calls whose per-rank frame counts are the
+    same on every rank; the key is the full count vector, so all ranks hit or miss together and the
+    collective set-up below stays collective."""
+    from .engine import BAProblem
+    key = (int(uvs_local.shape[0]), int(uvs_local.shape[2]), tuple(int(c) for c in counts), int(dev))
+    prob = _sharded.get(key)
+    if prob is None:
+        release_sharded_problem()
+        uid = broadcast_unique_id()
+        prob = BAProblem(uvs_local, calib_objpoints, device=dev, comm=(uid, rank(), world_size()))
+        _sharded[key] = prob
+    else:
+        prob.set_observations(uvs_local, calib_objpoints)
+    return prob
+
+
+def release_sharded_problem():
+    """Free the cached sharded problem and its communicator (call on every rank)."""
+    for old in _sharded.values():
+        old.close()
+    _sharded.clear()
+
+
 def solve_sharded(uvs_local, calib_objpoints, x0_local, **opt_kwargs):
     """Solve with frames sharded over the ranks of the default process group.
 
@@ -172,7 +200,6 @@ def solve_sharded(uvs_local, calib_objpoints, x0_local, **opt_kwargs):
     ranks' blocks), gathered over NVLink at the end of the solve and copied to the host on first access.
     """
     import torch
-    from .engine import BAProblem
     W, r = world_size(), rank()
     C, F_local = int(uvs_local.shape[0]), int(uvs_local.shape[1])
     counts = allreduce_sum(np.eye(W, dtype=np.int64)[r] * F_local)
@@ -181,8 +208,7 @@ def solve_sharded(uvs_local, calib_objpoints, x0_local, **opt_kwargs):
     start = int(counts[:r].sum())
     dev = local_device()
     torch.cuda.set_device(dev)
-    uid = broadcast_unique_id()
-    prob = BAProblem(uvs_local, calib_objpoints, device=dev, comm=(uid, r, W))
+    prob = _sharded_problem(uvs_local, calib_objpoints, dev, counts)
     nc = 12 * C
     try:
         x_loc, result = prob.solve(np.asarray(x0_local, dtype=np.float64), **opt_kwargs)
@@ -192,8 +218,9 @@ def solve_sharded(uvs_local, calib_objpoints, x0_local, **opt_kwargs):
         d_r, per_cam = prob.residuals_device(x_loc)
         parts = gather_device_vectors(d_r)
         per_cam_all = allreduce_sum(np.eye(W, dtype=np.int64)[r][:, None] * per_cam[None, :])   # (W, C)
-    finally:
-        prob.close()
+    except BaseException:
+        release_sharded_problem()     # a failed collective leaves the communicator unusable
+        raise
     poses = gather_arrays(x_loc[nc:])
     grads = gather_arrays(result.grad[nc:])
     x = merge_params(x_loc[:nc], poses)
