@@ -209,6 +209,10 @@ __device__ __forceinline__ void jac_row(const IntrReg& cam, const Proj& p, doubl
 }
 
 // One unit (camera, 32 frames): walk the N corners, both rows of each observation.
+#ifndef MCBA_K2P_VARIANT
+#define MCBA_K2P_VARIANT 0
+#endif
+#if MCBA_K2P_VARIANT == 0
 template <int kLoss>
 __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& cam, SrPtr sR,
                                              const double2* __restrict__ ob, const double* __restrict__ s_obj,
@@ -252,6 +256,131 @@ __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& 
     }
   }
 }
+
+#elif MCBA_K2P_VARIANT == 1
+// Variant 1: normalised image point (x, y) and inverse depth of corner n+1 are formed while corner n
+// accumulates (carried: 3 doubles).
+__device__ __forceinline__ void project_tail(const IntrReg& cam, double x, double y, double iz, Proj& o) {
+  o.iz = iz; o.x = x; o.y = y;
+  o.r2 = fma(o.x, o.x, o.y * o.y);
+  o.d = fma(o.r2, fma(cam.k2, o.r2, cam.k1), 1.0);
+  const double dp = fma(2.0 * cam.k2, o.r2, cam.k1);
+  o.pu = fma(cam.fx, o.x * o.d, cam.cx);
+  o.pv = fma(cam.fy, o.y * o.d, cam.cy);
+  const double xy2 = 2.0 * o.x * o.y * dp;
+  o.A00 = cam.fx * fma(2.0 * o.x * o.x, dp, o.d);
+  o.A01 = cam.fx * xy2;
+  o.A10 = cam.fy * xy2;
+  o.A11 = cam.fy * fma(2.0 * o.y * o.y, dp, o.d);
+  o.su = fma(o.A00, o.x, o.A01 * o.y);
+  o.sv = fma(o.A10, o.x, o.A11 * o.y);
+}
+__device__ __forceinline__ void point_xy(SrPtr sR, double qx, double qy, double qz, double& x, double& y, double& iz) {
+  const double X = fma(sR[0 * 32], qx, fma(sR[1 * 32], qy, fma(sR[2 * 32], qz, sR[9 * 32])));
+  const double Y = fma(sR[3 * 32], qx, fma(sR[4 * 32], qy, fma(sR[5 * 32], qz, sR[10 * 32])));
+  iz = inverse_depth(sR, qx, qy, qz);
+  x = X * iz;
+  y = Y * iz;
+}
+template <int kLoss>
+__device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& cam, SrPtr sR,
+                                             const double2* __restrict__ ob, const double* __restrict__ s_obj,
+                                             double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
+                                             double& cnt_acc) {
+  const int N = p.N;
+  double2 o0 = ob[0];
+  double2 o1 = N > 1 ? ob[kTile] : o0;
+  double xn, yn, izn;
+  point_xy(sR, s_obj[0], s_obj[1], s_obj[2], xn, yn, izn);
+#pragma unroll 1
+  for (int n = 0; n < N; ++n) {
+    const double2 cur = o0;
+    o0 = o1;
+    if (n + 2 < N) o1 = ob[(size_t)(n + 2) * kTile];
+    Proj pr;
+    project_tail(cam, xn, yn, izn, pr);
+    const int nn = n + 1 < N ? n + 1 : n;
+    point_xy(sR, s_obj[3 * nn], s_obj[3 * nn + 1], s_obj[3 * nn + 2], xn, yn, izn);
+    {
+      const bool hu = cur.x == cur.x;
+      const double fu = hu ? cur.x - pr.pu : 0.0;
+      double rho, wg, wh, au[10];
+      robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wh);
+      jac_row<true>(cam, pr, au);
+      cost_acc += rho;
+      sumsq_acc = fma(fu, fu, sumsq_acc);
+      cnt_acc += hu ? 1.0 : 0.0;
+      accumulate_row<true>(acc, au, wh, -wg * fu);
+    }
+    {
+      const bool hv = cur.y == cur.y;
+      const double fv = hv ? cur.y - pr.pv : 0.0;
+      double rho, wg, wh, av[10];
+      robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wh);
+      jac_row<false>(cam, pr, av);
+      cost_acc += rho;
+      sumsq_acc = fma(fv, fv, sumsq_acc);
+      cnt_acc += hv ? 1.0 : 0.0;
+      accumulate_row<false>(acc, av, wh, -wg * fv);
+    }
+  }
+}
+#elif MCBA_K2P_VARIANT == 2
+// Variant 2: the whole projection AND both robust weights of corner n+1 are formed while corner n
+// accumulates (carried: Proj + 4 weights).
+struct RowW { double wh, gf; };
+template <int kLoss>
+__device__ __forceinline__ void corner_front(const K2PParams& p, const IntrReg& cam, SrPtr sR, const double* __restrict__ s_obj,
+                                             int n, double2 cur, Proj& pr, RowW& wu, RowW& wv, double& cost_acc,
+                                             double& sumsq_acc, double& cnt_acc) {
+  const double iz = inverse_depth(sR, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2]);
+  project_shared(cam, sR, s_obj[3 * n], s_obj[3 * n + 1], s_obj[3 * n + 2], iz, pr);
+  {
+    const bool hu = cur.x == cur.x;
+    const double fu = hu ? cur.x - pr.pu : 0.0;
+    double rho, wg;
+    robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wu.wh);
+    wu.gf = -wg * fu;
+    cost_acc += rho;
+    sumsq_acc = fma(fu, fu, sumsq_acc);
+    cnt_acc += hu ? 1.0 : 0.0;
+  }
+  {
+    const bool hv = cur.y == cur.y;
+    const double fv = hv ? cur.y - pr.pv : 0.0;
+    double rho, wg;
+    robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wv.wh);
+    wv.gf = -wg * fv;
+    cost_acc += rho;
+    sumsq_acc = fma(fv, fv, sumsq_acc);
+    cnt_acc += hv ? 1.0 : 0.0;
+  }
+}
+template <int kLoss>
+__device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& cam, SrPtr sR,
+                                             const double2* __restrict__ ob, const double* __restrict__ s_obj,
+                                             double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
+                                             double& cnt_acc) {
+  const int N = p.N;
+  double2 o1 = N > 1 ? ob[kTile] : ob[0];
+  Proj pr;
+  RowW wu, wv;
+  corner_front<kLoss>(p, cam, sR, s_obj, 0, ob[0], pr, wu, wv, cost_acc, sumsq_acc, cnt_acc);
+#pragma unroll 1
+  for (int n = 0; n < N; ++n) {
+    // past the last corner the look-ahead runs on a missing observation: it adds nothing to the sums
+    const double2 nxt = n + 1 < N ? o1 : make_double2(nan(""), nan(""));
+    if (n + 2 < N) o1 = ob[(size_t)(n + 2) * kTile];
+    double au[10], av[10];
+    jac_row<true>(cam, pr, au);
+    jac_row<false>(cam, pr, av);
+    const RowW cu = wu, cv = wv;
+    corner_front<kLoss>(p, cam, sR, s_obj, n + 1 < N ? n + 1 : n, nxt, pr, wu, wv, cost_acc, sumsq_acc, cnt_acc);
+    accumulate_row<true>(acc, au, cu.wh, cu.gf);
+    accumulate_row<false>(acc, av, cv.wh, cv.gf);
+  }
+}
+#endif
 
 // The same walk for a HALF unit (16 frames): lanes 0-15 take the first half of the corners of
 // their frame, lanes 16-31 the second half of the same frames; the two partial blocks are added

@@ -5,7 +5,10 @@
 // Math: SURVEY.md Appendix A ("Schur form for this problem").
 #include <cstdlib>
 
+#include <cstring>
+
 #include "k2_common.cuh"
+#include "mcba_peer.cuh"
 
 namespace mcba {
 
@@ -367,19 +370,36 @@ int launch_k2_syrk(mcba_handle* h) {
 }
 
 // ------------------------------------------------------------------ finalize
-// Block (c, c'), c <= c':  S0_cc' = T_c^T ( [c==c'] U_raw,c - (Z Z^T)_cc' ) T_c'
-// T_c = [[I6,0,0],[0,Jl,0],[0,[t]x Jl,I3]]  (rows raw [intr | m | G], cols true [intr | r | t]).
+// ONE kernel from the per-CTA partial sums of K2p / K2c / SYRK to the packed reduced camera system
+// on every rank:
+//   reduce    CTA (c, c'), c <= c', adds the partials of ITS 12x12 block of sum Z Z^T (and, on the
+//             diagonal, of U_raw, g_raw and Z y) in a fixed order -- 1024 threads, all loads of a
+//             thread independent;
+//   basis     S0_cc' = T_c^T ( [c==c'] U_raw,c - (Z Z^T)_cc' ) T_c'  with
+//             T_c = [[I6,0,0],[0,Jl,0],[0,[t]x Jl,I3]]  (rows raw [intr | m | G], cols true [intr | r | t]);
+//   exchange  (multi-GPU, peer memory) the block goes straight from shared memory into slot [rank] of
+//             every peer, the CTA publishes its flag, waits for the same CTA of the other ranks and
+//             adds the slots in rank order (mcba_peer.cuh): no second launch, no round trip through
+//             d_red, no grid-wide counter;
+//   store     both mirror entries of the symmetric system, b, g_cam, diag(U), the scalars.
+// The last CTA handles the scalars (cost, sum f^2, count, max |g_pose| per rank).
+constexpr int kFinThreads = 1024;
+constexpr int kFinGS = 7;    // partial groups of the 144-element block sum   (7 x 144 = 1008 threads)
+constexpr int kFinGU = 8;    // partial groups of the 128-slot U / g sum      (8 x 128 = 1024)
+constexpr int kFinGZ = 64;   // partial groups of the 12-element Z y sum      (64 x 12 = 768)
+
 struct FinalizeParams {
-  int C, nc, nc8, nPartScal, rank;
+  int C, nc, nc8, rank;
   const CamConst* cams;
-  const double* Sraw;      // [nc8][nc8] sum Z Z^T, upper 8x8 block triangle valid (reduced over CTAs)
-  const double* Zy;        // [nc] sum Z y (reduced over tiles)
-  const double* Uraw;      // [C][kAcc] camera blocks / gradients, raw basis (reduced over CTAs)
-  const double* partS;     // [nPartScal][kRsNum]  (K2p: cost, sum f^2, count)
-  const double* partG;     // [nPartG] max |pose gradient| per tile (K2c)
-  long long nPartG;
+  const double* partSyrk; int nPartSyrk;   // [nPartSyrk][nc8 * nc8], upper 8x8 block triangle valid
+  const double* partU; int nPartU;         // [nPartU][C][kAcc]
+  const double* partZy; int nPartZy;       // [nPartZy][nc]
+  const double* partS;                     // [nPartU][kRsNum]  (K2p: cost, sum f^2, count)
+  const double* partG; long long nPartG;   // [nPartG] max |pose gradient| per K2c partial
   double* red;
   long long offS, offB, offG, offDiag, offScal, offRank;
+  int exchange;                            // 1: sum over ranks through peer memory (pv valid)
+  PeerView pv;
 };
 
 __device__ __forceinline__ void build_T(const CamConst& cam, double* T /*[144]*/, int tid) {
@@ -392,56 +412,167 @@ __device__ __forceinline__ void build_T(const CamConst& cam, double* T /*[144]*/
   }
 }
 
-__global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
-  __shared__ double M[144], X[144], Tc[144], Tp[144], vec[24];
+// fixed-order sum of partials g, g + G, g + 2G, ... of one element (8 independent loads in flight)
+__device__ __forceinline__ double strided_partial_sum(const double* __restrict__ src, size_t stride, int np, int g, int G) {
+  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int p = g;
+  for (; p + 7 * G < np; p += 8 * G) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(p + G * u) * stride);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    if (p + u * G < np) a[u] += __ldcg(src + (size_t)(p + G * u) * stride);
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+// vals[i] <- sum over ranks of vals[i], exchanged at offset off[i] of the slots (off < 0: not exchanged;
+// no-op without peers); vals/off: this CTA's outputs in shared memory
+__device__ __forceinline__ void exchange_values(const FinalizeParams& p, double* vals, const int* off, int n, int cta) {
+  if (!p.exchange) return;
+  const PeerView& pv = p.pv;
+  for (int s = 0; s < pv.nranks; ++s) {
+    double* dst = peer_slot_of(pv, (pv.rank + s) % pv.nranks);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (off[i] >= 0) dst[off[i]] = vals[i];
+  }
+  peer_publish(pv, cta);
+  peer_wait(pv, cta);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (off[i] < 0) continue;
+    double acc = 0.0;
+    for (int r = 0; r < pv.nranks; ++r) acc += __ldcg(peer_slot_from(pv, r) + off[i]);
+    vals[i] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const FinalizeParams p) {
+  __shared__ double sm_red[kFinGU * kAcc];      // partial-group sums (largest: 8 x 128; Z y: 64 x 12; block: 7 x 144)
+  __shared__ double M[144], X[144], Tc[144], Tp[144], Ur[kAcc], vec[24];
+  __shared__ double vals[192];                  // this CTA's outputs: 144 block entries | diag 12 | g 12 | b 12
+  __shared__ int off[192];
   const int tid = threadIdx.x;
+  const int nPairs = p.C * (p.C + 1) / 2;
   const int blk = blockIdx.x;
-  if (blk == p.C * p.C) {  // scalars
+  if (blk == nPairs) {  // ---------------- scalars
     double a = 0, b = 0, k = 0, g = 0;
-    for (int i = tid; i < p.nPartScal; i += blockDim.x) {
+    for (int i = tid; i < p.nPartU; i += blockDim.x) {
       const double* s = p.partS + (size_t)i * kRsNum;
       a += s[kRsCost]; b += s[kRsSumSq]; k += s[kRsCount];
     }
     for (long long i = tid; i < p.nPartG; i += blockDim.x) g = fmax(g, p.partG[i]);
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, off);
-      b += __shfl_xor_sync(0xffffffffu, b, off);
-      k += __shfl_xor_sync(0xffffffffu, k, off);
-      g = fmax(g, __shfl_xor_sync(0xffffffffu, g, off));
+    for (int o = 16; o >= 1; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      k += __shfl_xor_sync(0xffffffffu, k, o);
+      g = fmax(g, __shfl_xor_sync(0xffffffffu, g, o));
     }
-    if ((tid & 31) == 0) { M[(tid >> 5) * 4] = a; M[(tid >> 5) * 4 + 1] = b; M[(tid >> 5) * 4 + 2] = k; M[(tid >> 5) * 4 + 3] = g; }
+    if ((tid & 31) == 0) { sm_red[(tid >> 5) * 4] = a; sm_red[(tid >> 5) * 4 + 1] = b; sm_red[(tid >> 5) * 4 + 2] = k; sm_red[(tid >> 5) * 4 + 3] = g; }
+    __syncthreads();
+    const int nv = kRsNum + kMaxRanks;
+    if (tid < nv) { vals[tid] = 0.0; off[tid] = (int)(tid < kRsNum ? p.offScal + tid : p.offRank + (tid - kRsNum)); }
     __syncthreads();
     if (tid == 0) {
       a = b = k = g = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += M[w * 4]; b += M[w * 4 + 1]; k += M[w * 4 + 2]; g = fmax(g, M[w * 4 + 3]); }
-      double* sc = p.red + p.offScal;
-      for (int i = 0; i < kRsNum; ++i) sc[i] = 0.0;
-      sc[kRsCost] = a; sc[kRsSumSq] = b; sc[kRsCount] = k;
-      for (int i = 0; i < kMaxRanks; ++i) p.red[p.offRank + i] = 0.0;
-      p.red[p.offRank + p.rank] = g;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sm_red[w * 4]; b += sm_red[w * 4 + 1]; k += sm_red[w * 4 + 2]; g = fmax(g, sm_red[w * 4 + 3]); }
+      vals[kRsCost] = a; vals[kRsSumSq] = b; vals[kRsCount] = k;
+      vals[kRsNum + p.rank] = g;
     }
+    __syncthreads();
+    exchange_values(p, vals, off, nv, blk);
+    if (tid < nv) p.red[off[tid]] = vals[tid];
     return;
   }
-  const int c = blk / p.C, cp = blk % p.C;
-  if (c > cp) return;
+  // ---------------- block (c, cp), c <= cp
+  int c = 0, rem = blk;
+  while (rem >= p.C - c) { rem -= p.C - c; ++c; }
+  const int cp = c + rem;
+  const bool diag = c == cp;
   build_T(p.cams[c], Tc, tid);
   build_T(p.cams[cp], Tp, tid);
-  double uraw = 0.0;
-  if (tid < 144) {
-    const int i = tid / 12, j = tid % 12;
-    const int r = 12 * c + i, q = 12 * cp + j;
+  // reduce: all of a thread's loads are issued before any of the CTA barriers below
+  double vS = 0.0, vU = 0.0, vZ = 0.0;
+  if (tid < 144 * kFinGS) {
+    const int e = tid % 144, g = tid / 144;
+    const int r = 12 * c + e / 12, q = 12 * cp + e % 12;
     // r <= q element-wise within a diagonal camera block is not guaranteed: pick the stored 8x8 tile
-    const double zz = (r / 8 <= q / 8) ? p.Sraw[(size_t)r * p.nc8 + q] : p.Sraw[(size_t)q * p.nc8 + r];
-    double s = -zz;
-    if (c == cp) {
-      const int slot = acc_slot(i, j);   // -1: structurally zero product (fx.fy, fx.cy, cx.fy, cx.cy)
-      if (slot >= 0) uraw = p.Uraw[(size_t)c * kAcc + slot];
-      s += uraw;
+    const size_t idx = (r / 8 <= q / 8) ? (size_t)r * p.nc8 + q : (size_t)q * p.nc8 + r;
+    vS = strided_partial_sum(p.partSyrk + idx, (size_t)p.nc8 * p.nc8, p.nPartSyrk, g, kFinGS);
+  }
+  if (diag) {
+    {
+      const int e = tid % kAcc, g = tid / kAcc;
+      vU = strided_partial_sum(p.partU + (size_t)c * kAcc + e, (size_t)p.C * kAcc, p.nPartU, g, kFinGU);
     }
-    M[tid] = s;
+    if (tid < 12 * kFinGZ) {
+      const int e = tid % 12, g = tid / 12;
+      vZ = strided_partial_sum(p.partZy + 12 * c + e, (size_t)p.nc, p.nPartZy, g, kFinGZ);
+    }
+  }
+  if (tid < 144 * kFinGS) sm_red[tid] = vS;
+  __syncthreads();
+  if (tid < 144) {
+    double t = 0.0;
+#pragma unroll
+    for (int g = 0; g < kFinGS; ++g) t += sm_red[g * 144 + tid];
+    M[tid] = -t;
   }
   __syncthreads();
+  if (diag) {
+    sm_red[tid] = vU;
+    __syncthreads();
+    if (tid < kAcc) {
+      double t = 0.0;
+#pragma unroll
+      for (int g = 0; g < kFinGU; ++g) t += sm_red[g * kAcc + tid];
+      Ur[tid] = t;
+    }
+    __syncthreads();
+    if (tid < 12 * kFinGZ) sm_red[tid] = vZ;
+    __syncthreads();
+    if (tid < 12) {
+      double t = 0.0;
+      for (int g = 0; g < kFinGZ; ++g) t += sm_red[g * 12 + tid];
+      const double graw = Ur[acc_slot_q(tid)];
+      vec[tid] = graw;
+      vec[12 + tid] = graw - t;
+    }
+    double uraw = 0.0;
+    if (tid < 144) {
+      const int slot = acc_slot(tid / 12, tid % 12);   // -1: structurally zero product (fx.fy, fx.cy, cx.fy, cx.cy)
+      if (slot >= 0) uraw = Ur[slot];
+      M[tid] += uraw;
+    }
+    __syncthreads();
+    // diag(T^T U_raw T), b, g_cam: X = U_raw T
+    if (tid < 144) {
+      const int i = tid / 12, j = tid % 12;
+      double s = 0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int sl = acc_slot(i, k);
+        s += (sl >= 0 ? Ur[sl] : 0.0) * Tc[k * 12 + j];
+      }
+      X[tid] = s;
+    }
+    __syncthreads();
+    if (tid < 12) {
+      double d = 0, g = 0, b = 0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        d += Tc[k * 12 + tid] * X[k * 12 + tid];
+        g += Tc[k * 12 + tid] * vec[k];
+        b += Tc[k * 12 + tid] * vec[12 + k];
+      }
+      vals[144 + tid] = d; off[144 + tid] = (int)(p.offDiag + 12 * c + tid);
+      vals[156 + tid] = g; off[156 + tid] = (int)(p.offG + 12 * c + tid);
+      vals[168 + tid] = b; off[168 + tid] = (int)(p.offB + 12 * c + tid);
+    }
+    __syncthreads();
+  }
+  // S0 = Tc^T M Tp
   if (tid < 144) {
     const int i = tid / 12, j = tid % 12;
     double s = 0;
@@ -455,118 +586,53 @@ __global__ void __launch_bounds__(160) finalize_kernel(const FinalizeParams p) {
     double s = 0;
 #pragma unroll
     for (int k = 0; k < 12; ++k) s += Tc[k * 12 + i] * X[k * 12 + j];
-    const int r = 12 * c + i, q = 12 * cp + j;
-    if (c != cp || i <= j) {   // diagonal blocks: one thread writes both mirror entries (exact symmetry)
+    // diagonal blocks: only the (i <= j) entry is exchanged, kept and mirrored (exact symmetry)
+    vals[tid] = s;
+    off[tid] = (diag && i > j) ? -1 : (int)(p.offS + (size_t)(12 * c + i) * p.nc + 12 * cp + j);
+  }
+  __syncthreads();
+  const int nv = diag ? 180 : 144;
+  exchange_values(p, vals, off, nv, blk);
+  if (tid < 144) {
+    const int i = tid / 12, j = tid % 12;
+    if (!diag || i <= j) {
+      const double s = vals[tid];
+      const int r = 12 * c + i, q = 12 * cp + j;
       p.red[p.offS + (size_t)r * p.nc + q] = s;
       p.red[p.offS + (size_t)q * p.nc + r] = s;
     }
-  }
-  if (c != cp) return;
-  // diagonal block extras: diag(T^T U_raw T), b, g_cam
-  __syncthreads();
-  if (tid < 144) M[tid] = uraw;
-  if (tid >= 144 && tid < 156) {
-    const int i = tid - 144;
-    const double graw = p.Uraw[(size_t)c * kAcc + acc_slot_q(i)];
-    const double zy = p.Zy[12 * c + i];
-    vec[i] = graw;
-    vec[12 + i] = graw - zy;
-  }
-  __syncthreads();
-  if (tid < 144) {
-    const int i = tid / 12, j = tid % 12;
-    double s = 0;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) s += M[i * 12 + k] * Tc[k * 12 + j];
-    X[tid] = s;
-  }
-  __syncthreads();
-  if (tid < 12) {
-    double d = 0, g = 0, b = 0;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      d += Tc[k * 12 + tid] * X[k * 12 + tid];
-      g += Tc[k * 12 + tid] * vec[k];
-      b += Tc[k * 12 + tid] * vec[12 + k];
-    }
-    p.red[p.offDiag + 12 * c + tid] = d;
-    p.red[p.offG + 12 * c + tid] = g;
-    p.red[p.offB + 12 * c + tid] = b;
+  } else if (diag && tid < 180) {
+    p.red[off[tid]] = vals[tid];
   }
 }
 
-// Deterministic sum over partial buffers: out[e] = sum_p part[p][e] for up to two concatenated
-// segments.  kEl elements x kPg partial-groups per 256-thread CTA (wide segments with few
-// partials use 64 x 4, the narrow per-tile Z y sums with thousands of partials 8 x 32), 8
-// independent loads in flight per thread, fixed summation order.
-struct ReduceSeg {
-  const double* part;
-  int n_part, len;
-};
-template <int kEl, int kPg>
-__global__ void __launch_bounds__(256) reduce_partials_kernel(ReduceSeg s0, ReduceSeg s1, ReduceSeg s2,
-                                                              double* __restrict__ out) {
-  static_assert(kEl * kPg == 256, "one thread per (element, partial group)");
-  __shared__ double sm[kPg][kEl];
-  const int el = threadIdx.x % kEl, pg = threadIdx.x / kEl;
-  const int e = blockIdx.x * kEl + el;
-  double v = 0.0;
-  const int total = s0.len + s1.len + s2.len;
-  if (e < total) {
-    const ReduceSeg sg = e < s0.len ? s0 : (e < s0.len + s1.len ? s1 : s2);
-    const double* src = sg.part + (e < s0.len ? e : (e < s0.len + s1.len ? e - s0.len : e - s0.len - s1.len));
-    const int np = sg.n_part;
-    const size_t stride = (size_t)sg.len;
-    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int p = pg;
-    for (; p + 7 * kPg < np; p += 8 * kPg) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(p + kPg * u) * stride);
-    }
-    for (; p < np; p += kPg) a[0] += __ldcg(src + (size_t)p * stride);
-    v = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-  }
-  sm[pg][el] = v;
-  __syncthreads();
-  if (pg == 0 && e < total) {
-    double t = 0.0;
-#pragma unroll
-    for (int g = 0; g < kPg; ++g) t += sm[g][el];
-    out[e] = t;
-  }
-}
-
-int launch_finalize(mcba_handle* h) {
+int launch_finalize(mcba_handle* h, bool exchange) {
   const Layout& L = h->L;
   FinalizeParams p;
-  p.C = L.C; p.nc = L.nc; p.nc8 = L.nc8;
-  const int lenS = L.nc8 * L.nc8, lenZy = L.nc, lenU = L.C * kAcc;
-  {
-    // d_Sraw = [S (nc8^2) | U (C kAcc) | Z y (nc)]
-    const ReduceSeg s0{h->d_partSyrk, h->grid_syrk, lenS};
-    const ReduceSeg s1{h->d_partU, h->grid_frames, lenU};
-    const ReduceSeg s2{h->d_partZy, h->n_part_c, lenZy};   // one launch for all three segments
-    reduce_partials_kernel<16, 16><<<(lenS + lenU + lenZy + 15) / 16, 256, 0, h->stream>>>(s0, s1, s2, h->d_Sraw);
-    h->launches += 1;
-    MCBA_CUDA(cudaGetLastError());
-  }
-  p.Sraw = h->d_Sraw;
-  p.Uraw = h->d_Sraw + lenS;
-  p.Zy = h->d_Sraw + lenS + lenU;
-  p.nPartScal = h->grid_frames; p.rank = h->rank;
-  p.cams = h->d_cams; p.partS = h->d_partS; p.partG = h->d_partG; p.nPartG = h->n_part_c;
+  p.C = L.C; p.nc = L.nc; p.nc8 = L.nc8; p.rank = h->rank;
+  p.cams = h->d_cams;
+  p.partSyrk = h->d_partSyrk; p.nPartSyrk = h->grid_syrk;
+  p.partU = h->d_partU; p.nPartU = h->grid_frames;
+  p.partZy = h->d_partZy; p.nPartZy = h->n_part_c;
+  p.partS = h->d_partS; p.partG = h->d_partG; p.nPartG = h->n_part_c;
   p.red = h->d_red;
   p.offS = L.offS; p.offB = L.offB; p.offG = L.offG; p.offDiag = L.offDiag; p.offScal = L.offScal; p.offRank = L.offRank;
-  finalize_kernel<<<L.C * L.C + 1, 160, 0, h->stream>>>(p);
+  p.exchange = exchange ? 1 : 0;
+  if (exchange) p.pv = peer_next_call(h);
+  else memset(&p.pv, 0, sizeof(p.pv));
+  finalize_kernel<<<L.C * (L.C + 1) / 2 + 1, kFinThreads, 0, h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
 }
 
 // ------------------------------------------------------------------ K3 back-substitution
-// delta_f = -L^-T (y_f + Z_f^T delta_raw),  x_new = x + delta.  CTA = 4 warps on one frame tile,
-// lane = frame: warp w sums its quarter of the camera rows of Z^T delta_raw with coalesced
-// 256-byte row loads, warp 0 finishes the 6x6 triangular solve and the step scalars.
+// delta_f = -L^-T (y_f + Z_f^T delta_raw),  x_new = x + delta.  One WARP per frame tile, lane = frame:
+// the warp streams the tile's Z block (12C rows x 6 x 256 bytes, read once, evict-first) with 36
+// independent coalesced row loads in flight per lane and keeps its six sums in registers; y, L^-1
+// and the Marquardt scaling of the tile are requested before the Z stream so their latency hides
+// behind it.  No CTA barrier in the tile loop: a tile's whole dependent chain belongs to one warp
+// and the other warps of the SM keep the memory pipe full (HBM bound: 576 B per (camera, frame)).
 constexpr int kBackWarps = 4;
 struct BackParams {
   int C, nc, rank;
@@ -584,7 +650,7 @@ struct BackParams {
 __global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackParams p) {
   extern __shared__ double smem[];
   double* draw = smem;                       // [nc] camera step in the raw basis
-  double* sv = draw + ((p.nc + 1) & ~1);     // [kBackWarps][6][32]
+  __shared__ double s_part[kBackWarps][4];
   __shared__ bool s_last;
   const int tid = threadIdx.x, nc = p.nc, lane = tid & 31, warp = tid >> 5;
   for (int r = tid; r < nc; r += blockDim.x) {
@@ -599,47 +665,53 @@ __global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackPara
   }
   __syncthreads();
   double dd = 0, xx = 0, gd = 0, dDd = 0;
-  const int r_begin = (nc * warp) / kBackWarps, r_end = (nc * (warp + 1)) / kBackWarps;
-  for (long long tile = blockIdx.x; tile < p.nTiles; tile += gridDim.x) {
+  for (long long tile = (long long)blockIdx.x * kBackWarps + warp; tile < p.nTiles; tile += (long long)gridDim.x * kBackWarps) {
+    const long long f = p.perm[tile * kTile + lane];
+    double v[6], li[21], d2[6];
+    {
+      const double* yo = p.y + (size_t)tile * 6 * kTile + lane;
+      const double* lo = p.Linv + (size_t)tile * 21 * kTile + lane;
+      const double* so = p.D2pose + (size_t)tile * 6 * kTile + lane;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { v[k] = yo[k * kTile]; d2[k] = so[k * kTile]; }
+#pragma unroll
+      for (int k = 0; k < 21; ++k) li[k] = lo[k * kTile];
+    }
     const double* z = p.Z + ((size_t)tile * nc) * 6 * kTile + lane;
     double s[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 4
-    for (int r = r_begin; r < r_end; ++r) {
+#pragma unroll 6
+    for (int r = 0; r < nc; ++r) {
       const double dr = draw[r];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s[k] = fma(z[(size_t)(r * 6 + k) * kTile], dr, s[k]);
+      for (int k = 0; k < 6; ++k) s[k] = fma(__ldcs(z + (size_t)(r * 6 + k) * kTile), dr, s[k]);
     }
+    if (f >= 0) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) sv[(warp * 6 + k) * 32 + lane] = s[k];
-    __syncthreads();
-    const long long f = p.perm[tile * kTile + lane];
-    if (warp == 0 && f >= 0) {
-      double v[6];
+      for (int k = 0; k < 6; ++k) v[k] += s[k];
+      double xo[6], gp[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        double t = p.y[(size_t)tile * 6 * kTile + k * kTile + lane];
-#pragma unroll
-        for (int w = 0; w < kBackWarps; ++w) t += sv[(w * 6 + k) * 32 + lane];
-        v[k] = t;
+      for (int k = 0; k < 6; k += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(p.x + (size_t)nc + (size_t)f * 6 + k);
+        const double2 g = *reinterpret_cast<const double2*>(p.gpose + (size_t)f * 6 + k);
+        xo[k] = a.x; xo[k + 1] = a.y; gp[k] = g.x; gp[k + 1] = g.y;
       }
-      const double* li = p.Linv + (size_t)tile * 21 * kTile + lane;
+      double xn[6];
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         double d = 0.0;
 #pragma unroll
-        for (int j = k; j < 6; ++j) d -= li[(j * (j + 1) / 2 + k) * kTile] * v[j];
-        const size_t xi = (size_t)nc + (size_t)f * 6 + k;
-        const double xo = p.x[xi];
-        p.x_new[xi] = xo + d;
-        double d2 = p.D2pose[(size_t)tile * 6 * kTile + k * kTile + lane];
-        if (d2 == 0.0) d2 = 1.0;
+        for (int j = k; j < 6; ++j) d -= li[j * (j + 1) / 2 + k] * v[j];
+        xn[k] = xo[k] + d;
+        const double sc = d2[k] == 0.0 ? 1.0 : d2[k];
         dd = fma(d, d, dd);
-        xx = fma(xo, xo, xx);
-        gd = fma(p.gpose[(size_t)f * 6 + k], d, gd);
-        dDd = fma(d2 * d, d, dDd);
+        xx = fma(xo[k], xo[k], xx);
+        gd = fma(gp[k], d, gd);
+        dDd = fma(sc * d, d, dDd);
       }
+#pragma unroll
+      for (int k = 0; k < 6; k += 2)
+        *reinterpret_cast<double2*>(p.x_new + (size_t)nc + (size_t)f * 6 + k) = make_double2(xn[k], xn[k + 1]);
     }
-    __syncthreads();
   }
   if (blockIdx.x == 0 && warp == 0) {
     for (int r = lane; r < nc; r += 32) {
@@ -655,21 +727,27 @@ __global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackPara
       }
     }
   }
-  // only warp 0 holds step scalars
-  if (warp == 0) {
+  // step scalars: lanes -> warp -> CTA (fixed order) -> per-CTA partial; the last CTA adds the partials
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      dd += __shfl_xor_sync(0xffffffffu, dd, off);
-      xx += __shfl_xor_sync(0xffffffffu, xx, off);
-      gd += __shfl_xor_sync(0xffffffffu, gd, off);
-      dDd += __shfl_xor_sync(0xffffffffu, dDd, off);
+  for (int off = 16; off >= 1; off >>= 1) {
+    dd += __shfl_xor_sync(0xffffffffu, dd, off);
+    xx += __shfl_xor_sync(0xffffffffu, xx, off);
+    gd += __shfl_xor_sync(0xffffffffu, gd, off);
+    dDd += __shfl_xor_sync(0xffffffffu, dDd, off);
+  }
+  if (lane == 0) { s_part[warp][0] = dd; s_part[warp][1] = xx; s_part[warp][2] = gd; s_part[warp][3] = dDd; }
+  __syncthreads();
+  if (tid == 0) {
+    double* o = p.part + (size_t)blockIdx.x * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kBackWarps; ++w) t += s_part[w][q];
+      o[q] = t;
     }
-    if (lane == 0) {
-      double* o = p.part + (size_t)blockIdx.x * 4;
-      o[0] = dd; o[1] = xx; o[2] = gd; o[3] = dDd;
-      __threadfence();
-      s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
-    }
+    __threadfence();
+    s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (s_last && warp == 0) {
@@ -703,7 +781,7 @@ int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda
   p.part = h->d_scal + 64 + 3 * 4096;                                     // [grid_back][4]
   p.counter = reinterpret_cast<unsigned int*>(h->d_scal + 33);
   p.out = h->d_scal + 8;
-  backsub_kernel<<<h->grid_back, kBackWarps * 32, sizeof(double) * (((L.nc + 1) & ~1) + kBackWarps * 6 * 32), h->stream>>>(p);
+  backsub_kernel<<<h->grid_back, kBackWarps * 32, sizeof(double) * ((L.nc + 1) & ~1), h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "mcba_internal.h"
+#include "mcba_peer.cuh"
 
 namespace mcba {
 
@@ -62,6 +63,15 @@ int allreduce_packed(mcba_handle* h, double* buf, long long n) {
   return MCBA_OK;
 }
 
+// partial sums -> packed reduced system in d_red, summed over the ranks: inside the finalize kernel
+// when the peer buffers are mapped, by ncclAllReduce behind it otherwise
+static int finalize_and_sum(mcba_handle* h) {
+  const bool peer = h->nranks > 1 && h->peer_ready;
+  int rc = launch_finalize(h, peer);
+  if (rc || peer) return rc;
+  return allreduce_packed(h, h->d_red, h->L.redLen);
+}
+
 // ------------------------------------------------------------------ evaluation helpers
 struct EvalOut {
   double cost, sumsq, count, gnorm;
@@ -82,8 +92,7 @@ static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, do
   if (prof) cudaEventRecord(ev[4], h->stream);
   if ((rc = launch_k2_syrk(h))) return rc;
   if (prof) cudaEventRecord(ev[2], h->stream);
-  if ((rc = launch_finalize(h))) return rc;
-  if ((rc = allreduce_packed(h, h->d_red, h->L.redLen))) return rc;
+  if ((rc = finalize_and_sum(h))) return rc;
   if (prof) { cudaEventRecord(ev[3], h->stream); h->prof_n++; }
   return MCBA_OK;
 }
@@ -93,12 +102,14 @@ static int evaluate_tail(mcba_handle* h, const double* x, double lambda) {
   int rc;
   if ((rc = launch_k2_consumer(h, x, lambda))) return rc;
   if ((rc = launch_k2_syrk(h))) return rc;
-  if ((rc = launch_finalize(h))) return rc;
-  return allreduce_packed(h, h->d_red, h->L.redLen);
+  return finalize_and_sum(h);
 }
 
-// out[0..2] = fixed-order sum over K2p's per-CTA partials {0.5 sum rho, sum f^2, count}
-__global__ void sum_scalars_kernel(const double* __restrict__ partS, int n, double* __restrict__ out) {
+// out[0..2] = fixed-order sum over K2p's per-CTA partials {0.5 sum rho, sum f^2, count}; with peers the
+// 12 step scalars out[0..11] (3 from here, 4 from the back-substitution) are then summed over the
+// ranks in the same launch (mcba_peer.cuh)
+__global__ void sum_scalars_kernel(const double* __restrict__ partS, int n, double* __restrict__ out, int exchange,
+                                   const PeerView pv) {
   __shared__ double s[3][32];
   const int lane = threadIdx.x;
   double a = 0, b = 0, k = 0;
@@ -109,11 +120,35 @@ __global__ void sum_scalars_kernel(const double* __restrict__ partS, int n, doub
   }
   s[0][lane] = a; s[1][lane] = b; s[2][lane] = k;
   __syncwarp();
+  double v = 0.0;
   if (lane < 3) {
-    double t = 0;
-    for (int i = 0; i < 32; ++i) t += s[lane][i];
-    out[lane] = t;
+    for (int i = 0; i < 32; ++i) v += s[lane][i];
+    out[lane] = v;
+  } else if (lane < 12) {
+    v = out[lane];
   }
+  if (!exchange) return;
+  if (lane < 12)
+    for (int r = 0; r < pv.nranks; ++r) peer_slot_of(pv, (pv.rank + r) % pv.nranks)[lane] = v;
+  peer_publish(pv, 0);
+  peer_wait(pv, 0);
+  if (lane < 12) {
+    double acc = 0.0;
+    for (int r = 0; r < pv.nranks; ++r) acc += __ldcg(peer_slot_from(pv, r) + lane);
+    out[lane] = acc;
+  }
+}
+
+// trial-point scalars of the LM loop: sum of K2p's partials (+ the sum over ranks)
+static int launch_sum_scalars(mcba_handle* h) {
+  const bool peer = h->nranks > 1 && h->peer_ready;
+  PeerView pv;
+  if (peer) pv = peer_next_call(h); else std::memset(&pv, 0, sizeof(pv));
+  sum_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_partS, h->grid_frames, h->d_scal, peer ? 1 : 0, pv);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  if (peer) return MCBA_OK;
+  return allreduce_packed(h, h->d_scal, 12);
 }
 
 static void swap_k2p_outputs(mcba_handle* h) {
@@ -223,7 +258,7 @@ static int create_impl(mcba_handle* h, int C, int64_t F, int N, int device) {
   h->n_part_c = k2_consumer_parts(L, h->n_sm, &h->k2c_ring);
   h->grid_syrk = syrk_grid(L.nc, F, h->n_sm);
   h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
-  h->grid_back = (int)std::min<long long>(L.nTiles, 8LL * h->n_sm);
+  h->grid_back = (int)std::min<long long>((L.nTiles + 3) / 4, 16LL * h->n_sm);   // backsub: one warp per tile, 4 warps per CTA
   const long long n = L.nc + 6 * F;
   auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8); };
 #define MCBA_ALLOC(ptr, count) MCBA_CUDA(alloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
@@ -298,7 +333,6 @@ int mcba_destroy(mcba_handle* h) {
   if (h->solver) cusolverDnDestroy(h->solver);
   for (int s = 0; s < kMaxRanks; ++s) if (h->peer_mapped[s]) cudaIpcCloseMemHandle(h->peer_mapped[s]);
   if (h->peer_block) cudaFree(h->peer_block);
-  if (h->peer_counter) cudaFree(h->peer_counter);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
                   h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT};
@@ -545,9 +579,7 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
     const bool guess_switch = irls && opt.hessian == MCBA_HESSIAN_AUTO && last_rel_reduction < 0.1;
     const int trial_loss = guess_switch ? (opt.loss & 0xff) : loss_code();
     if ((rc = launch_k2_producer(h, xt, trial_loss, opt.f_scale))) return rc;
-    sum_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_partS, h->grid_frames, h->d_scal);
-    h->launches++;
-    if ((rc = allreduce_packed(h, h->d_scal, 12))) return rc;
+    if ((rc = launch_sum_scalars(h))) return rc;
     double* hp = h->h_pinned + trial_off;
     MCBA_CUDA(cudaMemcpyAsync(hp, h->d_scal, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
     MCBA_CUDA(cudaMemcpyAsync(hp + 16, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));

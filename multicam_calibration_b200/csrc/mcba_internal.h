@@ -100,9 +100,9 @@ struct mcba_handle {
   // multi-GPU
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
-  // peer-memory all-reduce (mcba_peer.cu): exchange block = [flags 2 x kMaxRanks | slots 2 x nranks x cap]
+  // peer-memory exchange (mcba_peer.cu): exchange block = [flags 2 x nranks x nflag | slots 2 x nranks x cap]
   void* peer_block = nullptr;
-  unsigned int* peer_counter = nullptr;
+  int peer_nflag = 0;
   long long peer_cap = 0;
   double* peer_slots[mcba::kMaxRanks] = {};
   unsigned long long* peer_flags[mcba::kMaxRanks] = {};
@@ -162,7 +162,7 @@ int k2_producer_grid(const mcba::Layout& L, int n_sm, int* warps);
 int k2_consumer_parts(const mcba::Layout& L, int n_sm, bool* ring);
 int launch_k2_syrk(mcba_handle* h);
 int syrk_grid(int nc, long long F, int n_sm);
-int launch_finalize(mcba_handle* h);
+int launch_finalize(mcba_handle* h, bool exchange);   // exchange: sum over ranks inside the kernel (peer memory)
 int launch_jacobian_blocks(mcba_handle* h, const double* x, double* Jc, double* Jp);
 int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda);
 int allreduce_packed(mcba_handle* h, double* buf, long long n);

@@ -162,6 +162,12 @@ int main(int argc, char** argv) {
   run_variant<kLossLinear, 8>("linear, 8 warps", p, grid, H1, U1, Hn, Un, n_obs);
   set_groups(4);
   run_variant<kLossSoftL1, 4>("soft_l1, 4 warps", p, grid, H1, U1, Hn, Un, n_obs);
+  {
+    double hs = 0, us = 0;
+    for (double v : H0) hs += fabs(v);
+    for (double v : usum(U0)) us += fabs(v);
+    printf("checksum (8 warps, soft_l1): sum|H| %.15e  sum|U| %.15e  (variant %d)\n", hs, us, MCBA_K2P_VARIANT);
+  }
   cmp("H  4 warps vs 8 warps", H0, H1);
   cmp("U  4 warps vs 8 warps", usum(U0), usum(U1));
   return 0;
