@@ -238,6 +238,20 @@ int mcba_triangulate(int device, void* cuda_stream, const double* d_uvs, int n_c
                      int64_t n_points, const double* h_ext, const double* h_K,
                      const double* h_dist, double* d_points);
 
+/* ---- reprojection-error QC (the step after bundle_adjust; viz.py:155-177 plot_residuals) ----
+ * Per camera and frame whose N corners were all detected: undistort the detections (geometry.py:328-358),
+ * homography detections -> board plane as cv2.findHomography computes it (float32-rounded points,
+ * normalised DLT, <= 10 iterations of OpenCV's LM refinement; viz.py:166), cv2.perspectiveTransform of
+ * the distortion-free projections of the corners d_reproj (C,F,N,2) -- made with
+ * mcba_project_points_multi(dist = NULL) from mcba_embed_points, viz.py:159-163 -- into the board's own
+ * coordinates (:167-169), and the distance of every transferred corner to the true one (:171-174).
+ * d_uvs (C,F,N,2) NaN = missing, d_obj (N,3), h_K (C,3,3), h_dist (C,5);
+ * d_transformed (C,F,N,2) and d_err (C,F,N) are NaN for frames with a missing corner.  N <= 128. */
+int mcba_homography_transfer(int device, void* cuda_stream, const double* d_uvs, const double* d_reproj,
+                             const double* d_obj, int n_cameras, int64_t n_frames, int n_points,
+                             const double* h_K, const double* h_dist, double* d_transformed,
+                             double* d_err);
+
 /* Per-kernel device timing of the evaluation pass (CUDA events on the handle's stream).
  * Synchronises, returns in ms_out[4] the summed durations of {K2p corner walk, K2c per-frame
  * Schur, SYRK, finalize + all-reduce} over the n evaluations since the last call, resets the

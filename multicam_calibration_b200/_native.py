@@ -87,6 +87,7 @@ _SIGNATURES = {
     "mcba_pairwise_transform": (_I, [_I, _P, _P, _P, _L, ctypes.POINTER(_D), ctypes.POINTER(_L)]),
     "mcba_consensus_poses": (_I, [_I, _P, _P, _P, _I, _L, _P]),
     "mcba_transformation_vectors": (_I, [_I, _P, _P, _L, _I, _P]),
+    "mcba_homography_transfer": (_I, [_I, _P, _P, _P, _P, _I, _L, _I, _P, _P, _P, _P]),
     "mcba_upload": (_I, [_I, _P, _P, _P, ctypes.c_size_t]),
     "mcba_download": (_I, [_I, _P, _P, _P, ctypes.c_size_t]),
 }

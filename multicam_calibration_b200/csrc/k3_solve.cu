@@ -28,9 +28,13 @@ namespace mcba {
 
 #ifdef MCBA_SOLVE_TIMING
 __device__ long long g_solve_clk[8];
+#define MCBA_T0(name) const long long name = clock64()
+#define MCBA_ACC(i, t0) do { if (threadIdx.x == 0) g_solve_clk[i] += clock64() - (t0); } while (0)
 #define MCBA_STAMP(i) do { if (threadIdx.x == 0) g_solve_clk[i] = clock64(); } while (0)
 #else
 #define MCBA_STAMP(i) do {} while (0)
+#define MCBA_T0(name) do {} while (0)
+#define MCBA_ACC(i, t0) do {} while (0)
 #endif
 
 constexpr int kSolveThreads = 512;
@@ -45,15 +49,15 @@ __device__ __forceinline__ void solve_dmma(double& c0, double& c1, double a, dou
                : "d"(a), "d"(b));
 }
 
-// 1/sqrt(t), t > 0 in the normal range: MUFU.RSQ64H seed, one cubic and one quadratic correction
-// (non-positive or NaN t gives NaN / inf, which the pivot test reports)
+// 1/sqrt(t), t > 0 in the normal range: MUFU.RSQ64H seed (> 20 bits) and ONE third-order correction
+// (relative error ~ (5/16) e^3 < 2^-60); four dependent FP64 operations instead of the library's
+// slow path on the critical chain of every pivot.  Non-positive or NaN t gives NaN / inf, which the
+// pivot test reports.
 __device__ __forceinline__ double solve_rsqrt(double t) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
-  double e = fma(-t, y * y, 1.0);
-  y = fma(y * e, fma(0.375, e, 0.5), y);
-  e = fma(-t, y * y, 1.0);
-  return fma(0.5 * y, e, y);
+  const double e = fma(-t, y * y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
 struct SolveParams {
@@ -87,28 +91,29 @@ __global__ void __launch_bounds__(kSolveThreads, 1) solve_reduced_kernel(const S
     if (d2 == 0.0) d2 = 1.0;
     damp = p.lambda * d2;
   }
-  const int n_pk = n1p * (n1p + 1) / 2;
+  // rows i and n1p-1-i together hold n1p+1 entries: element e of the (n1p/2) x (n1p+1) rectangle of
+  // row pairs (no square root, nothing wasted)
+  const int n_pk = n1p * (n1p + 1) / 2, pw = n1p + 1;
   for (int base = 0; base < n_pk; base += 8 * kSolveThreads) {
     double v[8];
+    int at[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int e = base + u * kSolveThreads + tid;
       v[u] = 0.0;
+      at[u] = -1;
       if (e < n_pk) {
-        int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-        while (i * (i + 1) / 2 > e) --i;
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        const int j = e - i * (i + 1) / 2;
-        if (i < nc) v[u] = p.red[p.offS + (size_t)i * nc + j];
-        else if (i == nc) v[u] = j < nc ? -p.red[p.offB + j] : 1.0;
+        const int pr = e / pw, off = e - pr * pw;
+        const int i = off <= pr ? pr : n1p - 1 - pr, j = off <= pr ? off : off - pr - 1;
+        at[u] = pk(i, j);
+        if (i < nc) v[u] = __ldcg(p.red + p.offS + (size_t)i * nc + j);
+        else if (i == nc) v[u] = j < nc ? -__ldcg(p.red + p.offB + j) : 1.0;
         else v[u] = i == j ? 1.0 : 0.0;
       }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int e = base + u * kSolveThreads + tid;
-      if (e < n_pk) A[e] = v[u];
-    }
+    for (int u = 0; u < 8; ++u)
+      if (at[u] >= 0) A[at[u]] = v[u];
   }
   __syncthreads();
   MCBA_STAMP(1);
@@ -138,71 +143,73 @@ __global__ void __launch_bounds__(kSolveThreads, 1) solve_reduced_kernel(const S
       if (cc + 1 <= cr) acc[s][1] = A[pk(cr, cc + 1)];
     }
   }
-
   MCBA_STAMP(2);
+#ifdef MCBA_SOLVE_TIMING
+  if (tid == 0) { g_solve_clk[5] = 0; g_solve_clk[6] = 0; }
+#endif
   // ---- blocked Cholesky of the leading nc columns
   for (int k0 = 0; k0 < nc; k0 += 8) {
     const int w = nc - k0 < 8 ? nc - k0 : 8;   // pivot columns of this panel
-    const int i = k0 + tid;                    // one thread per row of the block column
-    const int rr = tid;                        // < 8: a row of the diagonal block itself
-    double a[36];
-    int bad = 0;
+    // One thread per row i >= k0 of the block column, straight-line code: every thread factors the
+    // 8 x 8 diagonal block in registers and solves ITS row against it (for a row of the block itself
+    // that solve reproduces the factor's row, so all rows run the same instructions).  A partial last
+    // panel (12C not a multiple of 8) is processed to the full width: its extra columns belong to the
+    // right-hand-side / padding rows, whose values nobody reads.
+    const int i = k0 + tid;
+    double x[8];
+    MCBA_T0(tp0);
     if (i < n1p) {
-      double x[8];
+      double a[36];
 #pragma unroll
       for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
           if (c <= r) a[pk(r, c)] = A[pk(k0 + r, k0 + c)];
-      double* row = A + pk(i, k0);
-      if (rr >= 8) {
+      const double* row = A + pk(i, k0);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = row[c];
-      }
+      for (int c = 0; c < 8; ++c) x[c] = (tid >= 8 || c <= tid) ? row[c] : 0.0;
+      int bad = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (j < w) {
-          const double d = a[pk(j, j)];
-          if (!(d > 0.0) && bad == 0) bad = k0 + j + 1;
-          const double inv = solve_rsqrt(d);
-          a[pk(j, j)] = d * inv;
+        const double d = a[pk(j, j)];
+        if (!(d > 0.0) && bad == 0 && j < w) bad = k0 + j + 1;
+        const double inv = solve_rsqrt(d);
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (r > j) a[pk(r, j)] *= inv;
+        for (int r = 0; r < 8; ++r)
+          if (r > j) a[pk(r, j)] *= inv;
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (r > j && c > j && c <= r) a[pk(r, c)] = fma(-a[pk(r, j)], a[pk(c, j)], a[pk(r, c)]);
-          if (rr >= 8) {   // own row against column j of the factor
-            double t = x[j];
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (c < j) t = fma(-x[c], a[pk(j, c)], t);
-            x[j] = t * inv;
-          }
-          if (rr == 0) s_inv[k0 + j] = inv;
-        }
-      }
-      if (rr >= 8) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) row[c] = x[c];
-      }
-    }
-    __syncthreads();
-    // the factored diagonal block goes back only now: until the barrier the other warps were still
-    // reading the unfactored one (nobody reads it during the trailing update)
-    if (rr < 8) {
-      if (rr == 0 && bad && s_info == 0) s_info = bad;
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r == rr) {
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            if (c <= r) A[pk(k0 + r, k0 + c)] = a[pk(r, c)];
-        }
+            if (r > j && c > j && c <= r) a[pk(r, c)] = fma(-a[pk(r, j)], a[pk(c, j)], a[pk(r, c)]);
+        double t = x[j];           // own row against column j of the factor
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < j) t = fma(-x[c], a[pk(j, c)], t);
+        x[j] = t * inv;
+        if (tid == 0) s_inv[k0 + j] = inv;
+      }
+      if (tid == 0 && bad && s_info == 0) s_info = bad;
+      if (tid >= 8) {
+        double* wrow = A + pk(i, k0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) wrow[c] = x[c];
+      }
+    }
+    MCBA_ACC(5, tp0);
+    __syncthreads();
+    MCBA_T0(tp1);
+    // the rows of the diagonal block go back only now: until the barrier the other warps were still
+    // reading the unfactored block (nobody reads it during the trailing update)
+    if (tid < 8) {
+      double* wrow = A + pk(i, k0);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c <= tid) wrow[c] = x[c];
     }
     // trailing update on the FP64 tensor path: C_ij -= L_i L_j^T for this warp's tiles right of the panel
+    // (measured: jumping to the first live slot and batching the fragment loads of four tiles were
+    // both slower than this plain loop with a warp-uniform test per slot)
     const int kb = k0 >> 3;
     const int fk = k0 + (lane & 3);
 #pragma unroll
@@ -220,6 +227,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) solve_reduced_kernel(const S
         }
       }
     }
+    MCBA_ACC(6, tp1);
     __syncthreads();
   }
 
@@ -230,21 +238,20 @@ __global__ void __launch_bounds__(kSolveThreads, 1) solve_reduced_kernel(const S
     double y[kSlots];
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) y[s] = (lane + 32 * s) < nc ? A[pk(nc, lane + 32 * s)] : 0.0;
-    for (int j = nc - 1; j >= 0; --j) {
-      const int sj = j >> 5, lj = j & 31;
-      double yj = 0.0;
+    // 32 unknowns per register slot, slots from the last to the first (compile-time slot index: the
+    // carried chain of a step is broadcast -> multiply -> fused multiply-add, nothing else)
 #pragma unroll
-      for (int s = 0; s < kSlots; ++s)
-        if (s == sj) yj = y[s];
-      const double dj = __shfl_sync(0xffffffffu, yj, lj) * s_inv[j];
-      const double* Lj = A + pk(j, 0);
+    for (int sj = kSlots - 1; sj >= 0; --sj) {
+      const int j_hi = nc - 1 < 32 * sj + 31 ? nc - 1 : 32 * sj + 31;
+      for (int j = j_hi; j >= 32 * sj; --j) {
+        const double dj = __shfl_sync(0xffffffffu, y[sj], j & 31) * s_inv[j];
+        const double* Lj = A + pk(j, 0);
 #pragma unroll
-      for (int s = 0; s < kSlots; ++s) {
-        const int i = lane + 32 * s;
-        if (s <= sj) {
-          if (i < j) y[s] = fma(-Lj[i], dj, y[s]);
-          else if (i == j) y[s] = dj;
-        }
+        for (int s = 0; s < kSlots; ++s)
+          if (s < sj) y[s] = fma(-Lj[lane + 32 * s], dj, y[s]);
+        const int i = lane + 32 * sj;
+        const double l = i < j ? Lj[i] : 0.0;
+        y[sj] = i == j ? dj : fma(-l, dj, y[sj]);
       }
     }
 #pragma unroll
@@ -302,7 +309,7 @@ int solve_reduced(mcba_handle* h, double lambda) {
       long long c[8];
       cudaStreamSynchronize(h->stream);
       cudaMemcpyFromSymbol(c, g_solve_clk, sizeof(c));
-      fprintf(stderr, "solve phases (cycles): load %lld  setup %lld  panels %lld  backward %lld\n", c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3]);
+      fprintf(stderr, "solve phases (cycles): load %lld  setup %lld  panels %lld  backward %lld | factor (warp 0) %lld  update (warp 0) %lld\n", c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5], c[6]);
     }
 #endif
     h->launches++;

@@ -643,3 +643,142 @@ def lm_solve(x0, all_calib_uvs, calib_objpoints, ftol=1e-4, xtol=1e-8, gtol=1e-8
                 D2 = np.maximum(D2, np.diag(H))
     return x, dict(cost=cost, nfev=nfev, njev=njev, iterations=it, status=status,
                    optimality=float(np.abs(g).max()), grad=g, lam=lam)
+
+
+# --------------------------------------------------------------------------
+# reprojection-error QC: numeric core of viz.plot_residuals (viz.py:155-177)
+# --------------------------------------------------------------------------
+FLT_EPS = float(np.finfo(np.float32).eps)
+
+
+def homography_dlt(src, dst):
+    """First half of ``cv2.findHomography(src, dst)`` with ``method=0`` (viz.py:166).
+
+    OpenCV is an un-vendored binary dependency (4.13.0 in the build container); this restates the
+    documented algorithm of calib3d's ``HomographyEstimatorCallback::runKernel``: both point sets are
+    converted to float32, centred and scaled by the mean absolute deviation per axis, the 9x9
+    normal matrix of the DLT rows ``[X Y 1 0 0 0 -xX -xY -x]`` / ``[0 0 0 X Y 1 -yX -yY -y]`` is
+    accumulated and its eigenvector of the smallest eigenvalue, de-normalised and divided by
+    ``H[2,2]``, is the estimate.  Returns ``(H0, src32, dst32)`` (the rounded points as float64).
+    Pinned numerically against cv2 through ``tests/golden/qc.npz``.
+    """
+    M = np.asarray(src, dtype=np.float32).astype(np.float64)
+    m = np.asarray(dst, dtype=np.float32).astype(np.float64)
+    n = len(M)
+    cM, cm = M.sum(0) / n, m.sum(0) / n
+    sM, sm = n / np.abs(M - cM).sum(0), n / np.abs(m - cm).sum(0)
+    X, x = (M - cM) * sM, (m - cm) * sm
+    L = np.zeros((2 * n, 9))
+    L[0::2, 0], L[0::2, 1], L[0::2, 2] = X[:, 0], X[:, 1], 1.0
+    L[0::2, 6], L[0::2, 7], L[0::2, 8] = -x[:, 0] * X[:, 0], -x[:, 0] * X[:, 1], -x[:, 0]
+    L[1::2, 3], L[1::2, 4], L[1::2, 5] = X[:, 0], X[:, 1], 1.0
+    L[1::2, 6], L[1::2, 7], L[1::2, 8] = -x[:, 1] * X[:, 0], -x[:, 1] * X[:, 1], -x[:, 1]
+    H0 = np.linalg.eigh(L.T @ L)[1][:, 0].reshape(3, 3)
+    inv_norm = np.array([[1 / sm[0], 0, cm[0]], [0, 1 / sm[1], cm[1]], [0, 0, 1.0]])
+    norm2 = np.array([[sM[0], 0, -cM[0] * sM[0]], [0, sM[1], -cM[1] * sM[1]], [0, 0, 1.0]])
+    H = inv_norm @ H0 @ norm2
+    return H / H[2, 2], M, m
+
+
+def homography_residuals(h, M, m, want_jac=True):
+    """Reprojection residuals and Jacobian of the 8 free entries of H (``H[2,2] = 1``): OpenCV's
+    ``HomographyRefineCallback::compute``."""
+    ww = h[6] * M[:, 0] + h[7] * M[:, 1] + 1.0
+    ww = np.where(np.abs(ww) > EPS, 1.0 / np.where(ww == 0, 1.0, ww), 0.0)
+    xi = (h[0] * M[:, 0] + h[1] * M[:, 1] + h[2]) * ww
+    yi = (h[3] * M[:, 0] + h[4] * M[:, 1] + h[5]) * ww
+    r = np.empty(2 * len(M))
+    r[0::2], r[1::2] = xi - m[:, 0], yi - m[:, 1]
+    if not want_jac:
+        return r, None
+    J = np.zeros((2 * len(M), 8))
+    J[0::2, 0], J[0::2, 1], J[0::2, 2] = M[:, 0] * ww, M[:, 1] * ww, ww
+    J[0::2, 6], J[0::2, 7] = -M[:, 0] * ww * xi, -M[:, 1] * ww * xi
+    J[1::2, 3], J[1::2, 4], J[1::2, 5] = M[:, 0] * ww, M[:, 1] * ww, ww
+    J[1::2, 6], J[1::2, 7] = -M[:, 0] * ww * yi, -M[:, 1] * ww * yi
+    return r, J
+
+
+def homography_refine(H, M, m, max_iters=10, eps=FLT_EPS):
+    """Second half of ``cv2.findHomography`` for more than four points: OpenCV's ``LMSolver`` (calib3d
+    levmarq.cpp, Nash's Marquardt variant) on the reprojection error, at most 10 iterations, step and
+    residual tolerance FLT_EPSILON; damping ``lambda * diag(J^T J at the start)``, ``lambda`` starts
+    at 1, halves (to 0 below 0.75) after a good step and is rebuilt from ``1 / max diag(A^-1)`` after a
+    bad one."""
+    x = H.ravel()[:8].copy()
+    r, J = homography_residuals(x, M, m)
+    S = float(r @ r)
+    A, v = J.T @ J, J.T @ r
+    D = np.diag(A).copy()
+    lam, lc, it = 1.0, 0.75, 0
+    while True:
+        try:
+            d = np.linalg.solve(A + np.diag(lam * D), v)
+        except np.linalg.LinAlgError:
+            break
+        xd = x - d
+        rd, _ = homography_residuals(xd, M, m, want_jac=False)
+        Sd = float(rd @ rd)
+        dS = float(d @ (2.0 * v - A @ d))
+        R = (S - Sd) / (dS if abs(dS) > EPS else 1.0)
+        if R > 0.75:
+            lam *= 0.5
+            if lam < lc:
+                lam = 0.0
+        elif R < 0.25:
+            t = float(d @ v)
+            nu = min(max((Sd - S) / (t if abs(t) > EPS else 1.0) + 2.0, 2.0), 10.0)
+            if lam == 0.0:
+                try:
+                    lam = lc = 1.0 / max(EPS, float(np.abs(np.diag(np.linalg.inv(A))).max()))
+                except np.linalg.LinAlgError:
+                    break
+                nu *= 0.5
+            lam *= nu
+        if Sd < S:
+            S, x = Sd, xd
+            r, J = homography_residuals(x, M, m)
+            A, v = J.T @ J, J.T @ r
+        it += 1
+        if not (it < max_iters and np.abs(d).max() >= eps and np.abs(r).max() >= eps):
+            break
+    return np.append(x, 1.0).reshape(3, 3)
+
+
+def find_homography(src, dst):
+    """``cv2.findHomography(src, dst)[0]`` for N > 4 points, default method (viz.py:166)."""
+    H0, M, m = homography_dlt(src, dst)
+    return homography_refine(H0, M, m)
+
+
+def perspective_transform(points, H):
+    """``cv2.perspectiveTransform`` of (N,2) float64 points (viz.py:167-169): ``w = 1 / (H[2] . [x y 1])``
+    when ``|.| > eps``, else 0."""
+    p = np.asarray(points, dtype=float)
+    w = p @ H[2, :2] + H[2, 2]
+    w = np.where(np.abs(w) > EPS, 1.0 / np.where(w == 0, 1.0, w), 0.0)
+    return np.stack([(p @ H[0, :2] + H[0, 2]) * w, (p @ H[1, :2] + H[1, 2]) * w], axis=-1)
+
+
+def reprojection_transfer(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses):
+    """Numeric core of ``viz.plot_residuals`` (viz.py:155-177): per camera the distortion-free
+    projection of the board corners, the undistorted detections, and for every frame whose corners
+    were all detected the homography detections -> board plane, through which the projections are
+    carried into the board's own coordinates; the median distance to the true corners per camera.
+    Returns ``(median_error (C,), reprojections (C,F,N,2), transformed_reprojections (C,F,N,2))``."""
+    uvs = np.asarray(all_calib_uvs, dtype=float)
+    obj = np.asarray(calib_objpoints, dtype=float)
+    C, F, N, _ = uvs.shape
+    median_error = np.zeros(C)
+    reprojections = np.zeros((C, F, N, 2))
+    transformed = np.full((C, F, N, 2), np.nan)
+    pts = embed_calib_objpoints(obj, calib_poses)
+    for cam in range(C):
+        reprojections[cam] = project_points(pts, all_extrinsics[cam], all_intrinsics[cam][0])
+        und = undistort_points(uvs[cam], *all_intrinsics[cam])
+        valid = np.nonzero(~np.isnan(und).any((-1, -2)))[0]
+        for t in valid:
+            transformed[cam, t] = perspective_transform(reprojections[cam, t], find_homography(und[t], obj[:, :2]))
+        errors = np.linalg.norm(transformed[cam, valid] - obj[:, :2], axis=-1)
+        median_error[cam] = np.median(errors)
+    return median_error, reprojections, transformed

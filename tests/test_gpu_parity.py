@@ -637,3 +637,44 @@ def test_project_points_multi_matches_per_camera_projection():
     np.testing.assert_allclose(nodist[2], orc.project_points(pts, g["extrinsics"][2], intr[2][0], None), rtol=1e-12)
     with pytest.raises(ValueError):
         mcc.project_points_multi(pts, list(g["extrinsics"]), [(K, None if c else d) for c, (K, d) in enumerate(intr)])
+
+
+# ------------------------------------------------------------------ N3: reprojection-error QC (viz.py:155-177)
+def test_reprojection_residuals_vs_reference_and_oracle():
+    """mcba_homography_transfer against the output of the UNMODIFIED viz.plot_residuals (cv2.findHomography
+    per frame; tests/golden/qc.npz) and against the oracle's restatement of the same algorithm."""
+    from test_io_qc_cpu import compare_transfer, qc_fixture
+    d, intr = qc_fixture()
+    med, rep, tr = mcc.reprojection_residuals(d["uvs"], d["ext"], intr, d["objpoints"], d["poses"])
+    np.testing.assert_allclose(rep, d["reprojections"], rtol=1e-12)
+    # reference: transferred corners within 1e-5 board units (mm) on >= 95 % of the frames cv2 fitted (its
+    # binary-only LM ends elsewhere on the few grazing-angle frames), medians over those frames to 1e-6
+    good, valid = compare_transfer(tr, med, d, frame_tol=1e-5, frac_required=0.95, median_rtol=1e-6)
+    assert valid >= 100
+    # oracle: the same arithmetic up to the eigen-solver and FMA contraction
+    med_o, _, tr_o = orc.reprojection_transfer(d["uvs"], d["ext"], intr, d["objpoints"], d["poses"])
+    assert np.array_equal(np.isnan(tr), np.isnan(tr_o))
+    ok = ~np.isnan(tr_o).any((-1, -2))
+    diff = np.abs(np.where(ok[..., None, None], tr - tr_o, 0.0)).max((-1, -2))
+    # (whether the refinement takes one more step when its last step is within rounding of FLT_EPSILON
+    # is decided differently on a few frames: those differ by the size of that last step)
+    assert (diff[ok] <= 1e-6).mean() >= 0.97 and diff[ok].max() <= 1e-4, np.sort(diff[ok])[-8:]
+    np.testing.assert_allclose(med, med_o, rtol=1e-3)
+    # frames with a missing corner stay NaN; nothing else does
+    missing = np.isnan(d["uvs"]).any((-1, -2))
+    assert np.array_equal(np.isnan(tr).all((-1, -2)), missing)
+
+
+def test_reprojection_residuals_exact_homography():
+    """Noise-free detections of a distortion-free rig: every transferred corner lands on its board corner
+    (float32 rounding of the inputs inside findHomography bounds the error) and the medians are ~0."""
+    sc = make_scene(4, 64, sigma=0.0, seed=2)
+    cams = sc.true_cams.copy()
+    cams[:, 4:6] = 0.0
+    from multicam_calibration_b200.synthetic import forward_model
+    uvs = forward_model(cams, sc.true_poses, sc.objpoints)
+    ext, intr = split_cams(cams)
+    med, rep, tr = mcc.reprojection_residuals(uvs, ext, intr, sc.objpoints, sc.true_poses)
+    np.testing.assert_allclose(rep, uvs, rtol=1e-11)
+    err = np.linalg.norm(tr - sc.objpoints[:, :2], axis=-1)
+    assert np.nanmax(err) < 5e-3 and np.all(med < 1e-3)
