@@ -228,7 +228,8 @@ static bool k1_use_chunks() {
 
 // finite scalars of every chunk (one warp per chunk, coalesced) + number of observed corners
 __global__ void count_chunks_kernel(const double2* __restrict__ ref, int C, long long F, int N, long long nBlk,
-                                    long long* __restrict__ counts, unsigned long long* __restrict__ n_obs) {
+                                    long long* __restrict__ counts, unsigned int* __restrict__ chunk_rows,
+                                    unsigned long long* __restrict__ n_obs) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -239,15 +240,20 @@ __global__ void count_chunks_kernel(const double2* __restrict__ ref, int C, long
     const long long nf = F - f0 < kChunkFrames ? F - f0 : kChunkFrames;
     const double2* p = ref + ((long long)c * F + f0) * N;
     int cnt = 0;
+    unsigned rows = 0;   // bit r: (camera, frame f0 + r) has at least one finite scalar
     for (long long i = lane; i < nf * N; i += 32) {
       const double2 o = p[i];
       const bool fu = o.x == o.x, fv = o.y == o.y;
       cnt += (fu ? 1 : 0) + (fv ? 1 : 0);
       obs += (fu | fv) ? 1 : 0;
+      if (fu | fv) rows |= 1u << (unsigned)(i / N);
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    if (lane == 0) counts[u] = cnt;
+    for (int off = 16; off >= 1; off >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+      rows |= __shfl_xor_sync(0xffffffffu, rows, off);
+    }
+    if (lane == 0) { counts[u] = cnt; chunk_rows[u] = rows; }
   }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) obs += __shfl_xor_sync(0xffffffffu, obs, off);
@@ -269,9 +275,11 @@ int ensure_row_offsets(mcba_handle* h) {
   MCBA_CUDA(cudaMemsetAsync(h->d_row_off, 0, sizeof(long long) * (groups + 1), h->stream));
   int grid = (int)((groups * 32 + 255) / 256 < 148 * 16 ? (groups * 32 + 255) / 256 : 148 * 16);
   if (grid < 1) grid = 1;
-  if (chunks)
+  if (chunks) {
+    if (!h->d_chunk_rows) MCBA_CUDA(cudaMalloc((void**)&h->d_chunk_rows, sizeof(unsigned int) * (size_t)(groups + 1)));
     count_chunks_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref), L.C, L.F, L.N, nBlk,
-                                                    h->d_row_off, d_nobs);
+                                                    h->d_row_off, h->d_chunk_rows, d_nobs);
+  }
   else
     count_groups_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double2*>(h->d_obs_ref), slots, groups,
                                                     h->d_row_off, d_nobs);
@@ -315,7 +323,8 @@ int ensure_row_offsets(mcba_handle* h) {
 template <bool kCompact>
 __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(const double* __restrict__ x, const double2* __restrict__ ref,
                                                               const double* __restrict__ obj,
-                                                              const long long* __restrict__ chunk_off, int C, long long F,
+                                                              const long long* __restrict__ chunk_off,
+                                                              const unsigned int* __restrict__ chunk_rows, int C, long long F,
                                                               int N, long long nBlk, double* __restrict__ out) {
   extern __shared__ __align__(16) double k1_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
@@ -368,15 +377,21 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
     __syncwarp();
     const int total = nf * N;
     const long long base = ((long long)c * F + f0) * N;     // first slot of the chunk
-    long long off = kCompact ? chunk_off[u] : 0;
+    // the chunk's residuals start at its scanned offset; positions inside the chunk are 32-bit
+    double* out_c = out + (kCompact ? chunk_off[u] : 0);
+    int off = 0;
+    // rows (camera, frame) without a single detection -- a camera that did not see the board -- are
+    // known from the counting pass: their 16 N bytes of NaN are not read again
+    const unsigned rows = kCompact ? chunk_rows[u] : 0u;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     constexpr int kU = 4;
     for (int i0 = 0; i0 < total; i0 += 32 * kU) {
       double2 o[kU];
 #pragma unroll
       for (int g = 0; g < kU; ++g) {
         const int i = i0 + g * 32 + lane;
-        o[g] = make_double2(0.0, 0.0);
-        if (kCompact && i < total) o[g] = ref[base + i];
+        o[g] = make_double2(qnan, qnan);
+        if (kCompact && i < total && ((rows >> __umulhi((unsigned)i, inv_n)) & 1u)) o[g] = ref[base + i];
       }
 #pragma unroll
       for (int g = 0; g < kU; ++g) {
@@ -404,9 +419,15 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
         }
         if (kCompact) {
           const unsigned bu = __ballot_sync(0xffffffffu, fu), bv = __ballot_sync(0xffffffffu, fv);
-          const long long pos = off + __popc(bu & lt) + __popc(bv & lt);
-          if (fu) out[pos] = ru;
-          if (fv) out[pos + (fu ? 1 : 0)] = rv;
+          const int pos = off + __popc(bu & lt) + __popc(bv & lt);
+          double* dst = out_c + pos;
+          // both scalars of a detection (the usual case) leave as one 16-byte store when aligned
+          if (fu && fv && ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0)) {
+            *reinterpret_cast<double2*>(dst) = make_double2(ru, rv);
+          } else {
+            if (fu) dst[0] = ru;
+            if (fv) dst[fu ? 1 : 0] = rv;
+          }
           off += __popc(bu) + __popc(bv);
         }
       }
@@ -428,10 +449,10 @@ static int launch_chunks(mcba_handle* h, const double* x, double* out, bool comp
   }
   if (compact)
     residual_chunks_kernel<true><<<(int)grid, warps * 32, smem, h->stream>>>(
-        x, reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obj, h->d_row_off, L.C, L.F, L.N, nBlk, out);
+        x, reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obj, h->d_row_off, h->d_chunk_rows, L.C, L.F, L.N, nBlk, out);
   else
-    residual_chunks_kernel<false><<<(int)grid, warps * 32, smem, h->stream>>>(x, nullptr, h->d_obj, nullptr, L.C, L.F, L.N, nBlk,
-                                                                             out);
+    residual_chunks_kernel<false><<<(int)grid, warps * 32, smem, h->stream>>>(x, nullptr, h->d_obj, nullptr, nullptr, L.C, L.F,
+                                                                             L.N, nBlk, out);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

@@ -87,18 +87,6 @@ __device__ __forceinline__ double lane_transpose_sum32(const double (&v)[kAcc], 
   return w[0];
 }
 
-// 1/z for finite z of either sign in the normal range: MUFU.RCP64H seed (20 bits) and the same
-// cubic + quadratic Newton sequence CUDA's own 1.0/z uses, without its special-case branch.
-__device__ __forceinline__ double fast_rcp(double z) {
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(z));
-  double e = fma(-z, y, 1.0);
-  e = fma(e, e, e);
-  y = fma(y, e, y);
-  e = fma(-z, y, 1.0);
-  return fma(y, e, y);
-}
-
 // 1/sqrt(t) for t >= 1: MUFU.RSQ64H seed, one cubic and one quadratic correction.
 __device__ __forceinline__ double fast_rsqrt(double t) {
   double y;
@@ -209,8 +197,12 @@ __device__ __forceinline__ void jac_row(const IntrReg& cam, const Proj& p, doubl
 }
 
 // One unit (camera, 32 frames): walk the N corners, both rows of each observation.
+// MCBA_K2P_VARIANT (A/B builds, scripts/ubench/Makefile): 0 = projection at the top of the iteration with only
+// the inverse depth one corner ahead; 1 (default) = the normalised image point of the next corner is formed
+// while the current one accumulates (-2.4 % on B200); 2 = the whole projection and both robust weights one
+// corner ahead (slower: the carried state spills).  All three give bit-identical sums.
 #ifndef MCBA_K2P_VARIANT
-#define MCBA_K2P_VARIANT 0
+#define MCBA_K2P_VARIANT 1
 #endif
 #if MCBA_K2P_VARIANT == 0
 template <int kLoss>

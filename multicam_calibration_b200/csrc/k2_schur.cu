@@ -627,13 +627,18 @@ int launch_finalize(mcba_handle* h, bool exchange) {
 }
 
 // ------------------------------------------------------------------ K3 back-substitution
-// delta_f = -L^-T (y_f + Z_f^T delta_raw),  x_new = x + delta.  One WARP per frame tile, lane = frame:
-// the warp streams the tile's Z block (12C rows x 6 x 256 bytes, read once, evict-first) with 36
-// independent coalesced row loads in flight per lane and keeps its six sums in registers; y, L^-1
-// and the Marquardt scaling of the tile are requested before the Z stream so their latency hides
-// behind it.  No CTA barrier in the tile loop: a tile's whole dependent chain belongs to one warp
-// and the other warps of the SM keep the memory pipe full (HBM bound: 576 B per (camera, frame)).
+// delta_f = -L^-T (y_f + Z_f^T delta_raw),  x_new = x + delta.  HBM bound: the kernel's work is to
+// stream Z once (576 B per (camera, frame)).  Persistent CTAs of four warps; every warp owns whole
+// frame tiles (lane = frame) and pulls its tile's Z block through its OWN ring of three 18 KB
+// shared-memory stages with bulk asynchronous copies (12 rows = one camera per stage, contiguous in
+// Z): 220 KB in flight per SM without a single register or a dependent global load, the warp's lane
+// 0 re-arms a stage as soon as the warp has consumed it (same warp: no empty barrier).  y, L^-1 and
+// the Marquardt scaling of the tile are requested before the stream so their latency hides behind
+// it; no CTA barrier in the tile loop.
 constexpr int kBackWarps = 4;
+constexpr int kBackRows = 12;                        // rows of Z per stage (12C is always a multiple)
+constexpr int kBackStages = 3;
+constexpr int kBackStageDoubles = kBackRows * 6 * kTile;
 struct BackParams {
   int C, nc, rank;
   long long F, nTiles;
@@ -647,12 +652,14 @@ struct BackParams {
   double* part; unsigned int* counter; double* out;  // out[0..3] = |dx|^2, |x|^2, g.dx, dx D2 dx
 };
 
-__global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackParams p) {
-  extern __shared__ double smem[];
-  double* draw = smem;                       // [nc] camera step in the raw basis
+__global__ void __launch_bounds__(kBackWarps * 32, 1) backsub_kernel(const BackParams p) {
+  extern __shared__ __align__(128) unsigned char bs_smem[];
+  __shared__ unsigned long long full_bar[kBackWarps][kBackStages];
   __shared__ double s_part[kBackWarps][4];
   __shared__ bool s_last;
   const int tid = threadIdx.x, nc = p.nc, lane = tid & 31, warp = tid >> 5;
+  double* ring = reinterpret_cast<double*>(bs_smem) + (size_t)warp * kBackStages * kBackStageDoubles;
+  double* draw = reinterpret_cast<double*>(bs_smem) + (size_t)kBackWarps * kBackStages * kBackStageDoubles;   // [nc] camera step, raw basis
   for (int r = tid; r < nc; r += blockDim.x) {
     const int c = r / 12, i = r % 12;
     const double* d = p.dcam + 12 * c;
@@ -663,9 +670,32 @@ __global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackPara
     else v = cam.tJ[(i - 9) * 3] * d[6] + cam.tJ[(i - 9) * 3 + 1] * d[7] + cam.tJ[(i - 9) * 3 + 2] * d[8] + d[i];
     draw[r] = v;
   }
+  if (lane == 0) {
+    for (int s = 0; s < kBackStages; ++s) mbar_init(&full_bar[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+
+  // this warp's tiles: gw, gw + W, ...; its stream of stages: (tile, camera) in order
+  const long long gw = (long long)blockIdx.x * kBackWarps + warp, W = (long long)gridDim.x * kBackWarps;
+  const int chunks = nc / kBackRows;
+  const long long my_tiles = p.nTiles > gw ? (p.nTiles - gw + W - 1) / W : 0;
+  const long long n_units = my_tiles * chunks;
+  auto issue = [&](long long q) {   // lane 0 only: stage q of this warp's stream
+    const long long tile = gw + (q / chunks) * W;
+    const int ch = (int)(q % chunks), s = (int)(q % kBackStages);
+    constexpr unsigned bytes = kBackStageDoubles * sizeof(double);
+    mbar_expect_tx(&full_bar[warp][s], bytes);
+    tma_load_1d(ring + (size_t)s * kBackStageDoubles, p.Z + ((size_t)tile * nc + (size_t)ch * kBackRows) * 6 * kTile, bytes,
+                &full_bar[warp][s]);
+  };
+  if (lane == 0)
+    for (long long q = 0; q < kBackStages && q < n_units; ++q) issue(q);
+
   double dd = 0, xx = 0, gd = 0, dDd = 0;
-  for (long long tile = (long long)blockIdx.x * kBackWarps + warp; tile < p.nTiles; tile += (long long)gridDim.x * kBackWarps) {
+  long long q = 0;
+  for (long long it = 0; it < my_tiles; ++it) {
+    const long long tile = gw + it * W;
     const long long f = p.perm[tile * kTile + lane];
     double v[6], li[21], d2[6];
     {
@@ -677,13 +707,21 @@ __global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackPara
 #pragma unroll
       for (int k = 0; k < 21; ++k) li[k] = lo[k * kTile];
     }
-    const double* z = p.Z + ((size_t)tile * nc) * 6 * kTile + lane;
     double s[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll 6
-    for (int r = 0; r < nc; ++r) {
-      const double dr = draw[r];
+    for (int ch = 0; ch < chunks; ++ch, ++q) {
+      const int st = (int)(q % kBackStages);
+      mbar_wait(&full_bar[warp][st], (unsigned)((q / kBackStages) & 1));
+      const double* z = ring + (size_t)st * kBackStageDoubles + lane;
+      const double* dr = draw + ch * kBackRows;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) s[k] = fma(__ldcs(z + (size_t)(r * 6 + k) * kTile), dr, s[k]);
+      for (int r = 0; r < kBackRows; ++r) {
+        const double w = dr[r];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s[k] = fma(z[(r * 6 + k) * kTile], w, s[k]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our reads of the stage precede the copy that refills it
+      __syncwarp();
+      if (lane == 0 && q + kBackStages < n_units) issue(q + kBackStages);
     }
     if (f >= 0) {
 #pragma unroll
@@ -740,11 +778,11 @@ __global__ void __launch_bounds__(kBackWarps * 32) backsub_kernel(const BackPara
   if (tid == 0) {
     double* o = p.part + (size_t)blockIdx.x * 4;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int qd = 0; qd < 4; ++qd) {
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < kBackWarps; ++w) t += s_part[w][q];
-      o[q] = t;
+      for (int w = 0; w < kBackWarps; ++w) t += s_part[w][qd];
+      o[qd] = t;
     }
     __threadfence();
     s_last = atomicAdd(p.counter, 1u) == gridDim.x - 1;
@@ -781,7 +819,9 @@ int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda
   p.part = h->d_scal + 64 + 3 * 4096;                                     // [grid_back][4]
   p.counter = reinterpret_cast<unsigned int*>(h->d_scal + 33);
   p.out = h->d_scal + 8;
-  backsub_kernel<<<h->grid_back, kBackWarps * 32, sizeof(double) * ((L.nc + 1) & ~1), h->stream>>>(p);
+  const size_t smem = sizeof(double) * ((size_t)kBackWarps * kBackStages * kBackStageDoubles + (size_t)((L.nc + 1) & ~1));
+  MCBA_CUDA(cudaFuncSetAttribute(backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  backsub_kernel<<<h->grid_back, kBackWarps * 32, smem, h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

@@ -258,7 +258,7 @@ static int create_impl(mcba_handle* h, int C, int64_t F, int N, int device) {
   h->n_part_c = k2_consumer_parts(L, h->n_sm, &h->k2c_ring);
   h->grid_syrk = syrk_grid(L.nc, F, h->n_sm);
   h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
-  h->grid_back = (int)std::min<long long>((L.nTiles + 3) / 4, 16LL * h->n_sm);   // backsub: one warp per tile, 4 warps per CTA
+  h->grid_back = (int)std::min<long long>((L.nTiles + 3) / 4, (long long)h->n_sm);   // backsub: persistent CTAs of 4 warps, whole tiles per warp
   const long long n = L.nc + 6 * F;
   auto alloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8); };
 #define MCBA_ALLOC(ptr, count) MCBA_CUDA(alloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count)))
@@ -335,7 +335,7 @@ int mcba_destroy(mcba_handle* h) {
   if (h->peer_block) cudaFree(h->peer_block);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
-                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT};
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT, h->d_chunk_rows};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {
     for (int i = 0; i < kProfEvents * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);

@@ -55,6 +55,7 @@ struct mcba_handle {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   long long* d_row_off = nullptr;  // exclusive scan of finite scalars per group of 32 (c,f,n) slots
+  unsigned int* d_chunk_rows = nullptr;   // [C * nBlk] per K1 chunk: rows (camera, frame) with at least one finite scalar (lazy)
   double* d_rowT = nullptr;        // [C*F][12] composed (camera o pose) transforms, K1 only (lazy)
   long long m = 0;                 // finite scalar residuals
   long long n_obs = 0;             // (c,f,n) with at least one finite scalar

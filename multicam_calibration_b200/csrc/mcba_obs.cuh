@@ -21,7 +21,7 @@ __device__ __forceinline__ void project(const Intr& in, const double Rcf[9], con
   const double X = fma(Rcf[0], qx, fma(Rcf[1], qy, fma(Rcf[2], qz, tcf[0])));
   const double Y = fma(Rcf[3], qx, fma(Rcf[4], qy, fma(Rcf[5], qz, tcf[1])));
   const double Z = fma(Rcf[6], qx, fma(Rcf[7], qy, fma(Rcf[8], qz, tcf[2])));
-  const double iz = 1.0 / Z;
+  const double iz = fast_rcp(Z);   // branch-free (K1 is bound by its instruction count, not by HBM)
   const double x = X * iz, y = Y * iz;
   const double r2 = fma(x, x, y * y);
   const double d = fma(r2, fma(in.k2, r2, in.k1), 1.0);

@@ -38,6 +38,11 @@ def main():
                     stalls[k[len(STALL):-len("_per_issue_active.ratio")]] = round(val, 3)
         out["stall_cycles_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1]))
         kernels.append(out)
+    if "--last-per-kernel" in sys.argv:   # one record per kernel: its last captured launch
+        last = {}
+        for k in kernels:
+            last[k["Kernel Name"]] = k
+        kernels = list(last.values())
     print(json.dumps({"command": command, "kernels": kernels}, indent=1))
 
 
