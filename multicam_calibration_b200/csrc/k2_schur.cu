@@ -372,9 +372,10 @@ int launch_k2_syrk(mcba_handle* h) {
 // ------------------------------------------------------------------ finalize
 // ONE kernel from the per-CTA partial sums of K2p / K2c / SYRK to the packed reduced camera system
 // on every rank:
-//   reduce    CTA (c, c'), c <= c', adds the partials of ITS 12x12 block of sum Z Z^T (and, on the
-//             diagonal, of U_raw, g_raw and Z y) in a fixed order -- 1024 threads, all loads of a
-//             thread independent;
+//   reduce    four CTAs per block (c, c'), c <= c', each add a quarter of the partials of the 12x12 block
+//             of sum Z Z^T (and, on the diagonal, of U_raw, g_raw and Z y) in a fixed order -- 1024
+//             threads, every load of a thread requested before anything waits (one memory round trip);
+//             the last of the four to finish adds the quarters in index order and goes on alone;
 //   basis     S0_cc' = T_c^T ( [c==c'] U_raw,c - (Z Z^T)_cc' ) T_c'  with
 //             T_c = [[I6,0,0],[0,Jl,0],[0,[t]x Jl,I3]]  (rows raw [intr | m | G], cols true [intr | r | t]);
 //   exchange  (multi-GPU, peer memory) the block goes straight from shared memory into slot [rank] of
@@ -384,9 +385,11 @@ int launch_k2_syrk(mcba_handle* h) {
 //   store     both mirror entries of the symmetric system, b, g_cam, diag(U), the scalars.
 // The last CTA handles the scalars (cost, sum f^2, count, max |g_pose| per rank).
 constexpr int kFinThreads = 1024;
+constexpr int kFinSplit = 4; // CTAs that share the partial sums of one block (the last one to finish goes on)
 constexpr int kFinGS = 7;    // partial groups of the 144-element block sum   (7 x 144 = 1008 threads)
 constexpr int kFinGU = 8;    // partial groups of the 128-slot U / g sum      (8 x 128 = 1024)
 constexpr int kFinGZ = 64;   // partial groups of the 12-element Z y sum      (64 x 12 = 768)
+constexpr int kFinVals = 144 + kAcc + 12;   // per block: sum Z Z^T block | U_raw, g_raw slots | Z y
 
 struct FinalizeParams {
   int C, nc, nc8, rank;
@@ -396,6 +399,8 @@ struct FinalizeParams {
   const double* partZy; int nPartZy;       // [nPartZy][nc]
   const double* partS;                     // [nPartU][kRsNum]  (K2p: cost, sum f^2, count)
   const double* partG; long long nPartG;   // [nPartG] max |pose gradient| per K2c partial
+  double* scratch;                         // [pairs][kFinSplit][kFinVals]
+  unsigned int* counter;                   // [pairs], zero between launches
   double* red;
   long long offS, offB, offG, offDiag, offScal, offRank;
   int exchange;                            // 1: sum over ranks through peer memory (pv valid)
@@ -412,18 +417,30 @@ __device__ __forceinline__ void build_T(const CamConst& cam, double* T /*[144]*/
   }
 }
 
-// fixed-order sum of partials g, g + G, g + 2G, ... of one element (8 independent loads in flight)
-__device__ __forceinline__ double strided_partial_sum(const double* __restrict__ src, size_t stride, int np, int g, int G) {
-  double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int p = g;
-  for (; p + 7 * G < np; p += 8 * G) {
+// Partials lo + g, lo + g + G, ... (< hi) of one element: the first eight are REQUESTED here (independent
+// loads, nothing waits on them yet) and summed by strided_sum_finish in a fixed order, so that a thread can
+// have the loads of several segments in flight at once.
+struct StridedLoads {
+  double a[8];
+  const double* src;
+  size_t stride;
+  int next, hi, G;
+};
+__device__ __forceinline__ void strided_sum_start(StridedLoads& L, const double* __restrict__ src, size_t stride, int lo, int hi,
+                                                  int g, int G) {
+  L.src = src; L.stride = stride; L.hi = hi; L.G = G;
+  int p = lo + g;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(p + G * u) * stride);
+  for (int u = 0; u < 8; ++u) L.a[u] = (p + u * G < hi) ? __ldcg(src + (size_t)(p + u * G) * stride) : 0.0;
+  L.next = p + 8 * G;
+}
+__device__ __forceinline__ double strided_sum_finish(StridedLoads& L) {
+  for (int p = L.next; p < L.hi; p += 8 * L.G) {   // more than eight per thread (many K2c partials): further rounds
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (p + u * L.G < L.hi) L.a[u] += __ldcg(L.src + (size_t)(p + u * L.G) * L.stride);
   }
-#pragma unroll
-  for (int u = 0; u < 8; ++u)
-    if (p + u * G < np) a[u] += __ldcg(src + (size_t)(p + G * u) * stride);
-  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  return ((L.a[0] + L.a[1]) + (L.a[2] + L.a[3])) + ((L.a[4] + L.a[5]) + (L.a[6] + L.a[7]));
 }
 
 // vals[i] <- sum over ranks of vals[i], exchanged at offset off[i] of the slots (off < 0: not exchanged;
@@ -452,10 +469,12 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
   __shared__ double M[144], X[144], Tc[144], Tp[144], Ur[kAcc], vec[24];
   __shared__ double vals[192];                  // this CTA's outputs: 144 block entries | diag 12 | g 12 | b 12
   __shared__ int off[192];
+  __shared__ bool s_last;
   const int tid = threadIdx.x;
   const int nPairs = p.C * (p.C + 1) / 2;
-  const int blk = blockIdx.x;
-  if (blk == nPairs) {  // ---------------- scalars
+  const int blk = blockIdx.x / kFinSplit, part = blockIdx.x % kFinSplit;
+  if (blk == nPairs) {  // ---------------- scalars (one CTA)
+    if (part != 0) return;
     double a = 0, b = 0, k = 0, g = 0;
     for (int i = tid; i < p.nPartU; i += blockDim.x) {
       const double* s = p.partS + (size_t)i * kRsNum;
@@ -481,71 +500,94 @@ __global__ void __launch_bounds__(kFinThreads, 1) finalize_kernel(const Finalize
       vals[kRsNum + p.rank] = g;
     }
     __syncthreads();
-    exchange_values(p, vals, off, nv, blk);
+    exchange_values(p, vals, off, nv, nPairs);
     if (tid < nv) p.red[off[tid]] = vals[tid];
     return;
   }
-  // ---------------- block (c, cp), c <= cp
+  // ---------------- block (c, cp), c <= cp; this CTA's quarter of the partials
   int c = 0, rem = blk;
   while (rem >= p.C - c) { rem -= p.C - c; ++c; }
   const int cp = c + rem;
   const bool diag = c == cp;
-  build_T(p.cams[c], Tc, tid);
-  build_T(p.cams[cp], Tp, tid);
-  // reduce: all of a thread's loads are issued before any of the CTA barriers below
-  double vS = 0.0, vU = 0.0, vZ = 0.0;
-  if (tid < 144 * kFinGS) {
+  // request every load of the thread before anything waits: block sum, and on the diagonal U / g and Z y
+  StridedLoads lS, lU, lZ;
+  const bool hasS = tid < 144 * kFinGS, hasZ = diag && tid < 12 * kFinGZ;
+  if (hasS) {
     const int e = tid % 144, g = tid / 144;
     const int r = 12 * c + e / 12, q = 12 * cp + e % 12;
     // r <= q element-wise within a diagonal camera block is not guaranteed: pick the stored 8x8 tile
     const size_t idx = (r / 8 <= q / 8) ? (size_t)r * p.nc8 + q : (size_t)q * p.nc8 + r;
-    vS = strided_partial_sum(p.partSyrk + idx, (size_t)p.nc8 * p.nc8, p.nPartSyrk, g, kFinGS);
+    strided_sum_start(lS, p.partSyrk + idx, (size_t)p.nc8 * p.nc8, p.nPartSyrk * part / kFinSplit,
+                      p.nPartSyrk * (part + 1) / kFinSplit, g, kFinGS);
   }
   if (diag) {
-    {
-      const int e = tid % kAcc, g = tid / kAcc;
-      vU = strided_partial_sum(p.partU + (size_t)c * kAcc + e, (size_t)p.C * kAcc, p.nPartU, g, kFinGU);
-    }
-    if (tid < 12 * kFinGZ) {
-      const int e = tid % 12, g = tid / 12;
-      vZ = strided_partial_sum(p.partZy + 12 * c + e, (size_t)p.nc, p.nPartZy, g, kFinGZ);
-    }
+    const int e = tid % kAcc, g = tid / kAcc;
+    strided_sum_start(lU, p.partU + (size_t)c * kAcc + e, (size_t)p.C * kAcc, p.nPartU * part / kFinSplit,
+                      p.nPartU * (part + 1) / kFinSplit, g, kFinGU);
   }
-  if (tid < 144 * kFinGS) sm_red[tid] = vS;
+  if (hasZ) {
+    const int e = tid % 12, g = tid / 12;
+    strided_sum_start(lZ, p.partZy + 12 * c + e, (size_t)p.nc, p.nPartZy * part / kFinSplit,
+                      p.nPartZy * (part + 1) / kFinSplit, g, kFinGZ);
+  }
+  double* mine = p.scratch + ((size_t)blk * kFinSplit + part) * kFinVals;
+  if (hasS) sm_red[tid] = strided_sum_finish(lS);
   __syncthreads();
   if (tid < 144) {
     double t = 0.0;
 #pragma unroll
     for (int g = 0; g < kFinGS; ++g) t += sm_red[g * 144 + tid];
-    M[tid] = -t;
+    mine[tid] = t;
   }
-  __syncthreads();
   if (diag) {
-    sm_red[tid] = vU;
+    __syncthreads();
+    sm_red[tid] = strided_sum_finish(lU);
     __syncthreads();
     if (tid < kAcc) {
       double t = 0.0;
 #pragma unroll
       for (int g = 0; g < kFinGU; ++g) t += sm_red[g * kAcc + tid];
-      Ur[tid] = t;
+      mine[144 + tid] = t;
     }
     __syncthreads();
-    if (tid < 12 * kFinGZ) sm_red[tid] = vZ;
+    if (hasZ) sm_red[tid] = strided_sum_finish(lZ);
     __syncthreads();
     if (tid < 12) {
       double t = 0.0;
       for (int g = 0; g < kFinGZ; ++g) t += sm_red[g * 12 + tid];
+      mine[144 + kAcc + tid] = t;
+    }
+  }
+  // the last of the block's kFinSplit CTAs to get here adds the quarters (in index order) and goes on
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(p.counter + blk, 1u) == kFinSplit - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) p.counter[blk] = 0;
+  const double* all = p.scratch + (size_t)blk * kFinSplit * kFinVals;
+  if (tid < kFinVals && (diag || tid < 144)) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < kFinSplit; ++r) t += __ldcg(all + (size_t)r * kFinVals + tid);
+    if (tid < 144) M[tid] = -t;
+    else if (tid < 144 + kAcc) Ur[tid - 144] = t;
+    else vec[12 + (tid - 144 - kAcc)] = t;      // Z y, combined with g_raw below
+  }
+  build_T(p.cams[c], Tc, tid);
+  build_T(p.cams[cp], Tp, tid);
+  __syncthreads();
+  if (diag) {
+    if (tid < 12) {
       const double graw = Ur[acc_slot_q(tid)];
       vec[tid] = graw;
-      vec[12 + tid] = graw - t;
+      vec[12 + tid] = graw - vec[12 + tid];
     }
-    double uraw = 0.0;
     if (tid < 144) {
       const int slot = acc_slot(tid / 12, tid % 12);   // -1: structurally zero product (fx.fy, fx.cy, cx.fy, cx.cy)
-      if (slot >= 0) uraw = Ur[slot];
-      M[tid] += uraw;
+      if (slot >= 0) M[tid] += Ur[slot];
     }
-    __syncthreads();
     // diag(T^T U_raw T), b, g_cam: X = U_raw T
     if (tid < 144) {
       const int i = tid / 12, j = tid % 12;
@@ -615,12 +657,13 @@ int launch_finalize(mcba_handle* h, bool exchange) {
   p.partU = h->d_partU; p.nPartU = h->grid_frames;
   p.partZy = h->d_partZy; p.nPartZy = h->n_part_c;
   p.partS = h->d_partS; p.partG = h->d_partG; p.nPartG = h->n_part_c;
+  p.scratch = h->d_fin_scratch; p.counter = h->d_fin_counter;
   p.red = h->d_red;
   p.offS = L.offS; p.offB = L.offB; p.offG = L.offG; p.offDiag = L.offDiag; p.offScal = L.offScal; p.offRank = L.offRank;
   p.exchange = exchange ? 1 : 0;
   if (exchange) p.pv = peer_next_call(h);
   else memset(&p.pv, 0, sizeof(p.pv));
-  finalize_kernel<<<L.C * (L.C + 1) / 2 + 1, kFinThreads, 0, h->stream>>>(p);
+  finalize_kernel<<<(L.C * (L.C + 1) / 2 + 1) * kFinSplit, kFinThreads, 0, h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;

@@ -288,6 +288,9 @@ static int create_impl(mcba_handle* h, int C, int64_t F, int N, int device) {
   MCBA_ALLOC(h->d_partZy, (size_t)L.nTiles * L.nc);
   MCBA_ALLOC(h->d_Sraw, (size_t)L.nc8 * L.nc8 + L.nc + (size_t)C * kAcc);
   MCBA_ALLOC(h->d_red, L.redLen);
+  MCBA_ALLOC(h->d_fin_scratch, (size_t)(C * (C + 1) / 2) * 4 * (144 + kAcc + 12));
+  MCBA_ALLOC(h->d_fin_counter, C * (C + 1) / 2 + 1);
+  MCBA_CUDA(cudaMemset(h->d_fin_counter, 0, sizeof(unsigned int) * (C * (C + 1) / 2 + 1)));
   MCBA_ALLOC(h->d_Sd, (size_t)L.nc * L.nc);
   MCBA_ALLOC(h->d_dcam, 2 * L.nc);
   MCBA_ALLOC(h->d_scal, 64 + 7 * 4096);
@@ -335,7 +338,7 @@ int mcba_destroy(mcba_handle* h) {
   if (h->peer_block) cudaFree(h->peer_block);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
                   h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
-                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT, h->d_chunk_rows};
+                  h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT, h->d_chunk_rows, h->d_fin_scratch, h->d_fin_counter};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {
     for (int i = 0; i < kProfEvents * kProfRing; ++i) cudaEventDestroy(h->prof_ev[i]);

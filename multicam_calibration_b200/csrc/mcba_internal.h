@@ -86,6 +86,8 @@ struct mcba_handle {
   double* d_partSyrk = nullptr;
   double* d_Sraw = nullptr;   // [nc8 x nc8 raw-basis sum Z Z^T (upper 8x8 tiles) | Z y (12C) | U partial sums (C x kAcc)]
   double* d_red = nullptr;    // packed reduced system (see Layout)
+  double* d_fin_scratch = nullptr;      // finalize: per block and quarter, the partial sums [pairs][4][144 + kAcc + 12]
+  unsigned int* d_fin_counter = nullptr; // finalize: arrivals per block (zero between launches)
   double* d_Sd = nullptr;     // damped copy handed to potrf
   double* d_dcam = nullptr;   // [delta_cam true (12C) | delta_cam raw (12C)]
   double* d_scal = nullptr;   // step scalars (device), partials

@@ -38,7 +38,7 @@ def same_on_all_ranks(a):
     return bool(torch.equal(lo, hi))
 
 
-for tag, nf in (("all", None), ("sub", 301)):
+for tag, nf in (("all", None), ("sub", 301), ("all again: cached problem and communicator", None)):
     np.random.seed(1000 + 17 * rank)                     # ranks disagree on purpose
     with contextlib.redirect_stdout(io.StringIO()) as buf:
         e, i, p, use, res = mcc.bundle_adjust(*args, n_frames=nf, ftol=1e-12, xtol=1e-12, verbose=0)
