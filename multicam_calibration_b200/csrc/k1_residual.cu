@@ -5,6 +5,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "mcba_internal.h"
 #include "mcba_obs.cuh"
@@ -385,21 +386,24 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
     const unsigned rows = kCompact ? chunk_rows[u] : 0u;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     constexpr int kU = 4;
-    for (int i0 = 0; i0 < total; i0 += 32 * kU) {
+    // four groups of 32 slots per step; a step that lies wholly inside the chunk runs without any
+    // bounds test (8 of the 9 steps of a full 32-frame x 35-corner chunk), the last one with them
+    auto step = [&](int i0, auto checked_tag) {
+      constexpr bool kChecked = decltype(checked_tag)::value;
       double2 o[kU];
 #pragma unroll
       for (int g = 0; g < kU; ++g) {
         const int i = i0 + g * 32 + lane;
         o[g] = make_double2(qnan, qnan);
-        if (kCompact && i < total && ((rows >> __umulhi((unsigned)i, inv_n)) & 1u)) o[g] = ref[base + i];
+        if (kCompact && (!kChecked || i < total) && ((rows >> __umulhi((unsigned)i, inv_n)) & 1u)) o[g] = ref[base + i];
       }
 #pragma unroll
       for (int g = 0; g < kU; ++g) {
         const int i = i0 + g * 32 + lane;
-        if (i0 + g * 32 >= total) break;   // warp-uniform
+        if (kChecked && i0 + g * 32 >= total) break;   // warp-uniform
         bool fu = false, fv = false;
         double ru = 0.0, rv = 0.0;
-        if (i < total) {
+        if (!kChecked || i < total) {
           const int row = (int)__umulhi((unsigned)i, inv_n);
           const int n = i - row * N;
           const double2* t = reinterpret_cast<const double2*>(s_T + row * 12);
@@ -431,7 +435,10 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
           off += __popc(bu) + __popc(bv);
         }
       }
-    }
+    };
+    int i0 = 0;
+    for (; i0 + 32 * kU <= total; i0 += 32 * kU) step(i0, std::false_type{});
+    if (i0 < total) step(i0, std::true_type{});
   }
 }
 

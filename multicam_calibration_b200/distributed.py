@@ -75,13 +75,28 @@ def broadcast_unique_id():
 
 
 def gather_arrays(local):
-    """All ranks receive the list of every rank's array (host objects; poses are small)."""
+    """All ranks receive the list of every rank's 1-D array (float64 / int64; poses, gradients, frame
+    indices).  NCCL groups: one padded ``all_gather_into_tensor`` over NVLink (no pickling); gloo
+    groups (CPU tests): host objects."""
+    a = np.asarray(local)
     if world_size() == 1:
-        return [np.asarray(local)]
+        return [a]
     dist = _dist()
-    out = [None] * world_size()
-    dist.all_gather_object(out, np.asarray(local))
-    return out
+    W = world_size()
+    if dist.get_backend() != "nccl" or a.dtype not in (np.float64, np.int64):
+        out = [None] * W
+        dist.all_gather_object(out, a)
+        return out
+    import torch
+    flat = np.ascontiguousarray(a).ravel()
+    n = allreduce_sum(np.eye(W, dtype=np.int64)[rank()] * flat.size)
+    cap = max(int(n.max()), 1)
+    mine = torch.zeros(cap, dtype=torch.float64 if a.dtype == np.float64 else torch.int64, device="cuda")
+    mine[:flat.size] = torch.from_numpy(flat).cuda()
+    full = torch.empty(W * cap, dtype=mine.dtype, device="cuda")
+    dist.all_gather_into_tensor(full, mine)
+    host = full.cpu().numpy()
+    return [host[r * cap: r * cap + int(n[r])].copy() for r in range(W)]
 
 
 def allreduce_sum(values):
