@@ -161,9 +161,10 @@ def _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_
     thing summed across ranks); rank 0 draws the random sub-sample of :293-296 and broadcasts it, so
     every rank sees the same ``use_frames`` whatever its RNG state.
 
-    Returns ``(use_frames, d_uvs_local)``: the kept frames (global indices, identical on all ranks)
-    and THIS rank's share of their observations on its device -- the kept frames of its own range
-    when all are used (nothing is re-uploaded), a balanced slice of the drawn sample otherwise."""
+    Returns ``(use_frames, d_uvs_local, frames_per_rank)``: the kept frames (global indices, identical
+    on all ranks), THIS rank's share of their observations on its device -- the kept frames of its own
+    range when all are used (nothing is re-uploaded), a balanced slice of the drawn sample otherwise --
+    and how many frames every rank holds."""
     from . import distributed
     torch = _native.require_cuda()
     lib = _native.load()
@@ -194,19 +195,27 @@ def _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_
                                 ptr(d_elig), counts))
     n_eligible, n_finite = (int(v) for v in distributed.allreduce_sum(np.array([counts[0], counts[1]], dtype=np.int64)))
     if outlier_threshold is None:
-        def local_histogram(prefix, prefix_bits):
+        import torch.distributed as dist
+        on_device = dist.get_backend() == "nccl"
+
+        def summed_histogram(prefix, prefix_bits):    # 256 counts of THIS pass, already summed over the ranks
             check(lib.mcba_key_histogram(dev, stream, ptr(d_err), d_err.numel(), ctypes.c_uint64(prefix), prefix_bits,
                                          ptr(d_hist)))
-            return d_hist.cpu().numpy()
-        threshold = 5.0 * distributed.global_nanmedian(local_histogram, n_finite)
+            if on_device:
+                dist.all_reduce(d_hist)               # on the device: one host round trip per pass
+                return d_hist.cpu().numpy()
+            return distributed.allreduce_sum(d_hist.cpu().numpy())
+        threshold = 5.0 * distributed.global_nanmedian(summed_histogram, n_finite, reduce=lambda a: np.asarray(a))
     else:
         threshold = outlier_threshold
     excluded = ctypes.c_int64()
     check(lib.mcba_apply_threshold(dev, stream, ptr(d_mean), ptr(d_elig), C, Fl, float(threshold), ptr(d_use),
                                    ctypes.byref(excluded)))
     use_local = torch.nonzero(d_use).ravel()
-    n_excluded = int(distributed.allreduce_sum(np.array([excluded.value], dtype=np.int64))[0])
-    use_frames = np.concatenate(distributed.gather_arrays(use_local.cpu().numpy().astype(np.int64) + a))
+    # one exchange: every rank's kept frames (global indices; exact in float64) and its excluded count
+    kept, excl = distributed.gather_concat([(use_local + a).to(torch.float64), np.array([float(excluded.value)])])
+    n_excluded = int(sum(float(e.cpu()[0]) for e in excl))
+    use_frames = np.concatenate([k.cpu().numpy() for k in kept]).astype(np.int64)
     if r == 0:
         print(f"Excluding {n_excluded} out of {len(use_frames)} frames "
               f"based on an outlier threshold of {threshold}")
@@ -214,7 +223,7 @@ def _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_
         out = torch.empty((C, int(use_local.numel()), N, 2), dtype=torch.float64, device=device)
         if use_local.numel():
             check(lib.mcba_gather_frames(dev, stream, ptr(d_uvs), C, Fl, N, ptr(use_local), int(use_local.numel()), ptr(out)))
-        return use_frames, out
+        return use_frames, out, np.array([int(k.numel()) for k in kept], dtype=np.int64)
     # random sub-sample (bundle_adjustment.py:293-296): drawn once, on rank 0, from ITS global numpy RNG
     chosen = np.random.choice(use_frames, n_frames, replace=False) if r == 0 else None
     chosen = distributed.broadcast_object(chosen)
@@ -223,7 +232,9 @@ def _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_
     out = torch.empty((C, len(mine), N, 2), dtype=torch.float64, device=device)
     if len(mine):
         _native.upload_into(out, uvs[:, mine])          # a shard of the (small) sample from the caller's array
-    return chosen, out
+    counts = np.array([distributed.shard_bounds(len(chosen), W, q)[1] - distributed.shard_bounds(len(chosen), W, q)[0]
+                       for q in range(W)], dtype=np.int64)
+    return chosen, out, counts
 
 
 def select_frames(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints, calib_poses,
@@ -268,13 +279,11 @@ def bundle_adjust(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints
     n_cameras = all_calib_uvs.shape[0]
     if distributed.world_size() > 1:
         # every rank uploads, scans and solves only its own frames; use_frames is rank-contiguous
-        use_frames, d_local = _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
-                                                     calib_poses, n_frames, outlier_threshold)
-        counts = distributed.allreduce_sum(np.eye(distributed.world_size(), dtype=np.int64)[distributed.rank()]
-                                           * int(d_local.shape[1]))
+        use_frames, d_local, counts = _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,
+                                                             calib_poses, n_frames, outlier_threshold)
         lo = int(counts[:distributed.rank()].sum())
         x0_local = serialize_params(all_extrinsics, all_intrinsics, calib_poses[use_frames[lo:lo + int(d_local.shape[1])]])
-        x, result = distributed.solve_sharded(d_local, calib_objpoints, x0_local, **opt_kwargs)
+        x, result = distributed.solve_sharded(d_local, calib_objpoints, x0_local, frames_per_rank=counts, **opt_kwargs)
         del d_local
     else:
         use_frames, d_uvs = _select_frames_device(all_calib_uvs, all_extrinsics, all_intrinsics, calib_objpoints,

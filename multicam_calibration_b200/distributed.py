@@ -175,6 +175,33 @@ def gather_device_vectors(local):
     return [full[r * cap: r * cap + int(n[r])] for r in range(W)]
 
 
+def gather_concat(vectors):
+    """ONE exchange for several per-rank vectors.  ``vectors``: the same number of 1-D float64 vectors on
+    every rank (CUDA tensors or numpy arrays, any lengths).  Returns, per vector, the list of every
+    rank's piece (CUDA tensors on NCCL groups -- one sum of the length table and one padded
+    ``all_gather_into_tensor`` over NVLink -- host tensors on gloo groups)."""
+    import torch
+    dist = _dist()
+    W, r = world_size(), rank()
+    if dist.get_backend() != "nccl":
+        host = [v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v, dtype=np.float64) for v in vectors]
+        out = [None] * W
+        dist.all_gather_object(out, host)
+        return [[torch.from_numpy(np.ascontiguousarray(out[q][k])) for q in range(W)] for k in range(len(vectors))]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    vs = [v if hasattr(v, "is_cuda") else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(dev) for v in vectors]
+    lens = np.zeros((W, len(vs)), dtype=np.int64)
+    lens[r] = [int(v.numel()) for v in vs]
+    lens = allreduce_sum(lens)
+    cap = max(int(lens.sum(axis=1).max()), 1)
+    mine = torch.zeros(cap, dtype=torch.float64, device=dev)
+    torch.cat([v.reshape(-1).to(torch.float64) for v in vs], out=mine[:int(lens[r].sum())])
+    full = torch.empty(W * cap, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(full, mine)
+    offs = np.concatenate([np.zeros((W, 1), dtype=np.int64), np.cumsum(lens, axis=1)], axis=1)
+    return [[full[q * cap + int(offs[q, k]): q * cap + int(offs[q, k + 1])] for q in range(W)] for k in range(len(vs))]
+
+
 _sharded = {}
 
 
@@ -203,21 +230,26 @@ def release_sharded_problem():
     _sharded.clear()
 
 
-def solve_sharded(uvs_local, calib_objpoints, x0_local, **opt_kwargs):
+def solve_sharded(uvs_local, calib_objpoints, x0_local, frames_per_rank=None, **opt_kwargs):
     """Solve with frames sharded over the ranks of the default process group.
 
     ``uvs_local`` (C,F_r,N,2): THIS rank's frames (numpy array or float64 CUDA tensor);
     ``x0_local``: the 12C camera parameters (identical on all ranks) followed by the poses of this
-    rank's frames.  Ranks may hold different numbers of frames (at least one each).  Returns
+    rank's frames.  Ranks may hold different numbers of frames (at least one each;
+    ``frames_per_rank``: the counts of all ranks when the caller already knows them).  Returns
     ``(x, result)``: the full solution, poses concatenated in rank order, on every rank;
     ``result.fun`` is the full residual vector in the reference's order
     (bundle_adjustment.py:97: camera-major, so every camera's block is the concatenation of the
-    ranks' blocks), gathered over NVLink at the end of the solve and copied to the host on first access.
+    ranks' blocks), gathered over NVLink at the end of the solve -- together with the poses and the
+    gradient, in one exchange -- and copied to the host on first access.
     """
     import torch
     W, r = world_size(), rank()
     C, F_local = int(uvs_local.shape[0]), int(uvs_local.shape[1])
-    counts = allreduce_sum(np.eye(W, dtype=np.int64)[r] * F_local)
+    counts = (np.asarray(frames_per_rank, dtype=np.int64) if frames_per_rank is not None
+              else allreduce_sum(np.eye(W, dtype=np.int64)[r] * F_local))
+    if counts.shape != (W,) or int(counts[r]) != F_local:
+        raise ValueError("frames_per_rank does not match this rank's frames")
     if counts.min() < 1:
         raise ValueError(f"every rank needs at least one frame (frames per rank: {counts.tolist()})")
     start = int(counts[:r].sum())
@@ -229,18 +261,17 @@ def solve_sharded(uvs_local, calib_objpoints, x0_local, **opt_kwargs):
         x_loc, result = prob.solve(np.asarray(x0_local, dtype=np.float64), **opt_kwargs)
         result["peer_memory"] = bool(getattr(prob, "peer_memory", False))
         result["collective"] = "peer" if result["peer_memory"] else "nccl"
-        # residuals at the solution: computed by every rank on its frames, gathered on the device
+        # residuals at the solution (computed by every rank on its frames), poses and pose gradients:
+        # one exchange; per_cam = residual scalars per camera, where a rank's block goes in the full vector
         d_r, per_cam = prob.residuals_device(x_loc)
-        parts = gather_device_vectors(d_r)
-        per_cam_all = allreduce_sum(np.eye(W, dtype=np.int64)[r][:, None] * per_cam[None, :])   # (W, C)
+        parts, poses, grads, per_cam_all = gather_concat([d_r, x_loc[nc:], result.grad[nc:], per_cam.astype(np.float64)])
+        per_cam_all = np.stack([p.cpu().numpy() for p in per_cam_all]).astype(np.int64)      # (W, C)
     except BaseException:
         release_sharded_problem()     # a failed collective leaves the communicator unusable
         raise
-    poses = gather_arrays(x_loc[nc:])
-    grads = gather_arrays(result.grad[nc:])
-    x = merge_params(x_loc[:nc], poses)
+    x = merge_params(x_loc[:nc], [p.cpu().numpy() for p in poses])
     result["x"] = x
-    result["grad"] = merge_params(result.grad[:nc], grads)
+    result["grad"] = merge_params(result.grad[:nc], [g.cpu().numpy() for g in grads])
     result["active_mask"] = np.zeros_like(x)
     result["shard"] = (start, start + F_local)
 

@@ -174,6 +174,9 @@ def _gloo_worker(rank, world, port, q):
         assert med == np.nanmedian(err)
         vec = distributed.gather_device_vectors(torch.arange(3 + rank, dtype=torch.float64) + 10 * rank)
         assert [v.tolist() for v in vec] == [[0.0, 1.0, 2.0], [10.0, 11.0, 12.0, 13.0]]
+        # several per-rank vectors in one exchange (residuals + poses + gradients of the sharded solve)
+        a_, b_ = distributed.gather_concat([torch.arange(2 + rank, dtype=torch.float64), np.array([float(rank)])])
+        assert [v.tolist() for v in a_] == [[0.0, 1.0], [0.0, 1.0, 2.0]] and [v.tolist() for v in b_] == [[0.0], [1.0]]
         if rank == 0:
             Hf, gf, cf = orc.normal_equations(x0, uvs, obj)
             Sf, bf = orc.reduced_camera_system(Hf, gf, C)
