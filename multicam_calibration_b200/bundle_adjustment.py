@@ -196,7 +196,7 @@ def _select_frames_sharded(all_calib_uvs, all_extrinsics, all_intrinsics, calib_
     n_eligible, n_finite = (int(v) for v in distributed.allreduce_sum(np.array([counts[0], counts[1]], dtype=np.int64)))
     if outlier_threshold is None:
         import torch.distributed as dist
-        on_device = dist.get_backend() == "nccl"
+        on_device = W > 1 and dist.get_backend() == "nccl"
 
         def summed_histogram(prefix, prefix_bits):    # 256 counts of THIS pass, already summed over the ranks
             check(lib.mcba_key_histogram(dev, stream, ptr(d_err), d_err.numel(), ctypes.c_uint64(prefix), prefix_bits,

@@ -183,6 +183,8 @@ def gather_concat(vectors):
     import torch
     dist = _dist()
     W, r = world_size(), rank()
+    if W == 1:
+        return [[v if hasattr(v, "cpu") else torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64))] for v in vectors]
     if dist.get_backend() != "nccl":
         host = [v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v, dtype=np.float64) for v in vectors]
         out = [None] * W

@@ -432,7 +432,8 @@ def test_sharded_front_end_equals_the_single_device_front_end(capsys):
         use_a = mcc.select_frames(uvs, ext, intr, obj, poses, n_frames=nf, outlier_threshold=thr)
         msg_a = capsys.readouterr().out.strip().splitlines()[0]
         np.random.seed(1)
-        use_b, d_local = ba._select_frames_sharded(uvs, ext, intr, obj, poses, nf, thr)
+        use_b, d_local, counts = ba._select_frames_sharded(uvs, ext, intr, obj, poses, nf, thr)
+        assert counts.tolist() == [len(use_b)]
         msg_b = capsys.readouterr().out.strip().splitlines()[0]
         assert np.array_equal(use_a, use_b) and msg_a == msg_b
         assert np.array_equal(d_local.cpu().numpy(), uvs[:, use_b], equal_nan=True)
