@@ -185,6 +185,34 @@ def test_many_cameras_reduced_system_matches_oracle():
         assert np.abs((x1 - x0) - step).max() < 1e-6 * np.abs(step).max()
 
 
+@pytest.mark.parametrize("C,F", [(1, 40), (2, 31), (3, 65), (5, 33), (7, 96), (12, 40)])
+def test_camera_count_sweep_step_and_solve(C, F):
+    """Every camera count takes its own variants of K2c (ring <= 6 cameras / general), of the SYRK tile
+    lists, of the finalize grid and of the solve kernel (12 C not a multiple of 8: partial last panel;
+    3 / 8 / 19 register tiles per warp): reduced system and damped step against the dense oracle, then
+    the LM loop down to the oracle's own minimum."""
+    sc = make_scene(C, F, sigma=0.3, p_missing_view=0.25 if C > 2 else 0.0, p_missing_corner=0.05, seed=40 + C)
+    x0 = sc.x0()
+    prob = mcc.BAProblem(sc.uvs, sc.objpoints)
+    lam = 1e-3
+    S, b, gcam, cost = prob.build_reduced(x0, lam=lam)
+    H, grad, cost_o = orc.normal_equations(x0, sc.uvs, sc.objpoints)
+    D2 = np.diag(H).copy()
+    D2[:12 * C] = 0.0
+    S_o, b_o = orc.reduced_camera_system(H, grad, C, lam, D2)
+    assert cost == pytest.approx(cost_o, rel=1e-12)
+    assert np.abs(S - S_o).max() < 1e-9 * np.abs(S_o).max()
+    assert np.abs(b - b_o).max() < 1e-9 * np.abs(b_o).max()
+    assert np.array_equal(S, S.T)
+    x1 = prob.solve_step(lam)
+    step = orc.lm_step(H, grad, C, lam, np.diag(H).copy())
+    assert np.abs((x1 - x0) - step).max() < 1e-6 * np.abs(step).max()
+    x, res = prob.solve(x0, ftol=1e-12, xtol=1e-12, verbose=0)
+    assert res.success
+    assert res.cost == pytest.approx(orc.robust_cost(x, sc.uvs, sc.objpoints), rel=1e-11)
+    assert res.cost < cost and res.rms < 0.4
+
+
 # ------------------------------------------------------------------ convergence
 @pytest.mark.parametrize("hessian", ["auto", "triggs", "irls"])
 def test_lm_loop_follows_the_dense_mirror(hessian):
