@@ -97,11 +97,14 @@ static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, do
   return MCBA_OK;
 }
 
-// K2c + SYRK + finalize (+ all-reduce) on the K2p outputs the handle currently points at
-static int evaluate_tail(mcba_handle* h, const double* x, double lambda) {
+// K2c + SYRK + finalize (+ all-reduce) on the K2p outputs the handle currently points at.
+// need_system = false: the evaluation that closes a solve only has to deliver the gradient, b and the
+// scalars at the final point -- the SYRK (sum Z Z^T, a fifth of an evaluation) is skipped and the S
+// part of d_red is left stale (nothing reads it before the next evaluation rebuilds it).
+static int evaluate_tail(mcba_handle* h, const double* x, double lambda, bool need_system = true) {
   int rc;
   if ((rc = launch_k2_consumer(h, x, lambda))) return rc;
-  if ((rc = launch_k2_syrk(h))) return rc;
+  if (need_system && (rc = launch_k2_syrk(h))) return rc;
   return finalize_and_sum(h);
 }
 
@@ -616,10 +619,11 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
       ++iter;
       if (irls && opt.hessian == MCBA_HESSIAN_AUTO && actual < 1e-2 * cost) irls = false;
       last_rel_reduction = actual / cost;
-      if (loss_code() != trial_loss) {   // the Gauss-Newton weights change here (once per solve): walk again
+      if (loss_code() != trial_loss && term == -2) {   // the Gauss-Newton weights change here (once per solve): walk again
         if ((rc = evaluate(h, x, lambda, loss_code(), opt.f_scale))) return rc;
       } else {
-        if ((rc = evaluate_tail(h, x, lambda))) return rc;
+        // (a step that ends the solve needs no new system: gradient and cost do not depend on the weights' variant)
+        if ((rc = evaluate_tail(h, x, lambda, term == -2))) return rc;
       }
       if ((rc = enqueue_eval_readback(h))) return rc;
       ++njev;
