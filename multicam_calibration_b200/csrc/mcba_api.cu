@@ -5,6 +5,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -111,8 +112,17 @@ static int evaluate_tail(mcba_handle* h, const double* x, double lambda, bool ne
 // out[0..2] = fixed-order sum over K2p's per-CTA partials {0.5 sum rho, sum f^2, count}; with peers the
 // 12 step scalars out[0..11] (3 from here, 4 from the back-substitution) are then summed over the
 // ranks in the same launch (mcba_peer.cuh)
+// Where the scalars go besides d_scal: a MAPPED pinned host block that the LM loop polls (no D2H copy
+// operations and no driver wait between the trial walk and the host's accept / reject decision).
+struct HostSignal {
+  double* vals;                  // [16]: the 12 step scalars, [12] = pivot info of the solve
+  unsigned long long* flag;      // written last, after a system-scope fence
+  unsigned long long seq;
+  const int* info;               // d_info of the solve kernel
+};
+
 __global__ void sum_scalars_kernel(const double* __restrict__ partS, int n, double* __restrict__ out, int exchange,
-                                   const PeerView pv) {
+                                   const PeerView pv, const HostSignal sig) {
   __shared__ double s[3][32];
   const int lane = threadIdx.x;
   double a = 0, b = 0, k = 0;
@@ -130,28 +140,64 @@ __global__ void sum_scalars_kernel(const double* __restrict__ partS, int n, doub
   } else if (lane < 12) {
     v = out[lane];
   }
-  if (!exchange) return;
-  if (lane < 12)
-    for (int r = 0; r < pv.nranks; ++r) peer_slot_of(pv, (pv.rank + r) % pv.nranks)[lane] = v;
-  peer_publish(pv, 0);
-  peer_wait(pv, 0);
-  if (lane < 12) {
-    double acc = 0.0;
-    for (int r = 0; r < pv.nranks; ++r) acc += __ldcg(peer_slot_from(pv, r) + lane);
-    out[lane] = acc;
+  if (exchange) {
+    if (lane < 12)
+      for (int r = 0; r < pv.nranks; ++r) peer_slot_of(pv, (pv.rank + r) % pv.nranks)[lane] = v;
+    peer_publish(pv, 0);
+    peer_wait(pv, 0);
+    if (lane < 12) {
+      double acc = 0.0;
+      for (int r = 0; r < pv.nranks; ++r) acc += __ldcg(peer_slot_from(pv, r) + lane);
+      out[lane] = acc;
+      v = acc;
+    }
+  }
+  if (sig.flag) {   // results straight into host memory, then the sequence number
+    if (lane < 12) sig.vals[lane] = v;
+    if (lane == 12) sig.vals[12] = (double)sig.info[0];
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sig.flag), "l"(sig.seq) : "memory");
   }
 }
 
 // trial-point scalars of the LM loop: sum of K2p's partials (+ the sum over ranks)
-static int launch_sum_scalars(mcba_handle* h) {
+static int launch_sum_scalars(mcba_handle* h, bool signal_host) {
   const bool peer = h->nranks > 1 && h->peer_ready;
+  const bool direct = signal_host && (peer || h->nranks == 1);   // NCCL sums behind the kernel: no direct signal
   PeerView pv;
   if (peer) pv = peer_next_call(h); else std::memset(&pv, 0, sizeof(pv));
-  sum_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_partS, h->grid_frames, h->d_scal, peer ? 1 : 0, pv);
+  HostSignal sig{nullptr, nullptr, 0, h->d_info};
+  if (direct) {
+    sig.vals = h->d_signal_vals;
+    sig.flag = h->d_signal_flag;
+    sig.seq = ++h->signal_seq;
+  }
+  sum_scalars_kernel<<<1, 32, 0, h->stream>>>(h->d_partS, h->grid_frames, h->d_scal, peer ? 1 : 0, pv, sig);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
-  if (peer) return MCBA_OK;
+  if (peer || h->nranks == 1) return MCBA_OK;
   return allreduce_packed(h, h->d_scal, 12);
+}
+
+// Spin until the scalar kernel of the current trial has written its sequence number into the mapped
+// host block (a few microseconds after the kernel ends, against tens for two D2H copies and a stream
+// synchronisation).  A failed launch / trapped kernel shows up in cudaStreamQuery.
+static int wait_host_signal(mcba_handle* h) {
+  volatile unsigned long long* flag = h->h_signal_flag;
+  unsigned spins = 0;
+  while (*flag != h->signal_seq) {
+    if ((++spins & 0x3fff) == 0) {
+      const cudaError_t q = cudaStreamQuery(h->stream);
+      if (q == cudaSuccess) { if (*flag == h->signal_seq) break; }
+      else if (q != cudaErrorNotReady) { set_error(std::string("LM loop: ") + cudaGetErrorString(q)); return MCBA_ERR_CUDA; }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return MCBA_OK;
 }
 
 static void swap_k2p_outputs(mcba_handle* h) {
@@ -184,6 +230,7 @@ static int enqueue_eval_readback(mcba_handle* h) {
   const Layout& L = h->L;
   const long long tail = L.redLen - L.offB;
   MCBA_CUDA(cudaMemcpyAsync(h->h_pinned, h->d_red + L.offB, sizeof(double) * tail, cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaEventRecord(h->readback_done, h->stream));   // parse_eval's caller waits on this (already complete by then)
   return MCBA_OK;
 }
 
@@ -305,6 +352,12 @@ static int create_impl(mcba_handle* h, int C, int64_t F, int N, int device) {
   MCBA_CUDA(cudaMemset(h->d_gpose, 0, sizeof(double) * L.Fpad * 6));
   MCBA_CUDA(cudaMemset(h->d_partSyrk, 0, sizeof(double) * (size_t)h->grid_syrk * L.nc8 * L.nc8));   // lower block triangle is never written
   MCBA_CUDA(cudaMallocHost((void**)&h->h_pinned, sizeof(double) * (L.redLen + 64)));
+  MCBA_CUDA(cudaHostAlloc((void**)&h->h_signal_vals, sizeof(double) * 32, cudaHostAllocMapped));
+  std::memset(h->h_signal_vals, 0, sizeof(double) * 32);
+  h->h_signal_flag = reinterpret_cast<unsigned long long*>(h->h_signal_vals + 16);
+  MCBA_CUDA(cudaHostGetDevicePointer((void**)&h->d_signal_vals, h->h_signal_vals, 0));
+  h->d_signal_flag = reinterpret_cast<unsigned long long*>(h->d_signal_vals + 16);
+  MCBA_CUDA(cudaEventCreateWithFlags(&h->readback_done, cudaEventDisableTiming));
   // the reduced system is solved by this library's own kernel (k3_solve.cu); a cuSOLVER handle is
   // only created if a system wider than 192 (more than 16 cameras) is ever solved
   return MCBA_OK;
@@ -348,6 +401,8 @@ int mcba_destroy(mcba_handle* h) {
     delete[] h->prof_ev;
   }
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->h_signal_vals) cudaFreeHost(h->h_signal_vals);
+  if (h->readback_done) cudaEventDestroy(h->readback_done);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MCBA_OK;
@@ -585,12 +640,20 @@ int mcba_lm_run(mcba_handle* h, double* d_x, const mcba_options* opt_in, mcba_re
     const bool guess_switch = irls && opt.hessian == MCBA_HESSIAN_AUTO && last_rel_reduction < 0.1;
     const int trial_loss = guess_switch ? (opt.loss & 0xff) : loss_code();
     if ((rc = launch_k2_producer(h, xt, trial_loss, opt.f_scale))) return rc;
-    if ((rc = launch_sum_scalars(h))) return rc;
+    const bool direct = h->nranks == 1 || h->peer_ready;
+    if ((rc = launch_sum_scalars(h, true))) return rc;
     double* hp = h->h_pinned + trial_off;
-    MCBA_CUDA(cudaMemcpyAsync(hp, h->d_scal, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
-    MCBA_CUDA(cudaMemcpyAsync(hp + 16, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
-    MCBA_CUDA(cudaStreamSynchronize(h->stream));
+    if (direct) {
+      if ((rc = wait_host_signal(h))) return rc;
+      for (int i = 0; i < 12; ++i) hp[i] = h->h_signal_vals[i];
+      reinterpret_cast<int*>(hp + 16)[0] = (int)h->h_signal_vals[12];
+    } else {   // NCCL fallback: the sum runs behind the kernel, read back the classic way
+      MCBA_CUDA(cudaMemcpyAsync(hp, h->d_scal, sizeof(double) * 12, cudaMemcpyDeviceToHost, h->stream));
+      MCBA_CUDA(cudaMemcpyAsync(hp + 16, h->d_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+      MCBA_CUDA(cudaStreamSynchronize(h->stream));
+    }
     if (pending) {
+      MCBA_CUDA(cudaEventSynchronize(h->readback_done));   // enqueued before this trial: complete, returns at once
       settle();
       if (status != -2) { swap_k2p_outputs(h); break; }   // converged at the current point: drop the trial
     }

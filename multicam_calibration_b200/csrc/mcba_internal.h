@@ -92,6 +92,13 @@ struct mcba_handle {
   double* d_dcam = nullptr;   // [delta_cam true (12C) | delta_cam raw (12C)]
   double* d_scal = nullptr;   // step scalars (device), partials
   double* h_pinned = nullptr; // pinned host mirror for small read-backs
+  // mapped pinned block the LM loop polls: [16 doubles | sequence flag]; device aliases of the same memory
+  double* h_signal_vals = nullptr;
+  unsigned long long* h_signal_flag = nullptr;
+  double* d_signal_vals = nullptr;
+  unsigned long long* d_signal_flag = nullptr;
+  unsigned long long signal_seq = 0;
+  cudaEvent_t readback_done = nullptr;
   int n_part_c = 0;           // K2c partial outputs (one per tile, or one per persistent CTA on the ring path)
   bool k2c_ring = false;
   int grid_frames = 0, prod_warps = 8, grid_syrk = 0, grid_cost = 0, grid_back = 0;
