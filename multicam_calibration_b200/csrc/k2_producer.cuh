@@ -207,12 +207,11 @@ __device__ __forceinline__ void jac_row(const IntrReg& cam, const Proj& p, doubl
 #if MCBA_K2P_VARIANT == 0
 template <int kLoss>
 __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& cam, SrPtr sR,
-                                             const double2* __restrict__ ob, const double* __restrict__ s_obj,
+                                             const double2* __restrict__ ob, double2 o0, double2 o1,
+                                             const double* __restrict__ s_obj,
                                              double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
                                              double& cnt_acc) {
   const int N = p.N;
-  double2 o0 = ob[0];
-  double2 o1 = N > 1 ? ob[kTile] : o0;
   double iz_next = inverse_depth(sR, s_obj[0], s_obj[1], s_obj[2]);
 #pragma unroll 1
   for (int n = 0; n < N; ++n) {
@@ -276,12 +275,12 @@ __device__ __forceinline__ void point_xy(SrPtr sR, double qx, double qy, double 
 }
 template <int kLoss>
 __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& cam, SrPtr sR,
-                                             const double2* __restrict__ ob, const double* __restrict__ s_obj,
+                                             const double2* __restrict__ ob, double2 o0, double2 o1,
+                                             const double* __restrict__ s_obj,
                                              double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
                                              double& cnt_acc) {
+  // o0, o1: the unit's first two observations, requested by the caller BEFORE its pose work
   const int N = p.N;
-  double2 o0 = ob[0];
-  double2 o1 = N > 1 ? ob[kTile] : o0;
   double xn, yn, izn;
   point_xy(sR, s_obj[0], s_obj[1], s_obj[2], xn, yn, izn);
 #pragma unroll 1
@@ -350,14 +349,14 @@ __device__ __forceinline__ void corner_front(const K2PParams& p, const IntrReg& 
 }
 template <int kLoss>
 __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& cam, SrPtr sR,
-                                             const double2* __restrict__ ob, const double* __restrict__ s_obj,
+                                             const double2* __restrict__ ob, double2 o0, double2 o1,
+                                             const double* __restrict__ s_obj,
                                              double (&acc)[kAcc], double& cost_acc, double& sumsq_acc,
                                              double& cnt_acc) {
   const int N = p.N;
-  double2 o1 = N > 1 ? ob[kTile] : ob[0];
   Proj pr;
   RowW wu, wv;
-  corner_front<kLoss>(p, cam, sR, s_obj, 0, ob[0], pr, wu, wv, cost_acc, sumsq_acc, cnt_acc);
+  corner_front<kLoss>(p, cam, sR, s_obj, 0, o0, pr, wu, wv, cost_acc, sumsq_acc, cnt_acc);
 #pragma unroll 1
   for (int n = 0; n < N; ++n) {
     // past the last corner the look-ahead runs on a missing observation: it adds nothing to the sums
@@ -391,15 +390,19 @@ __device__ __forceinline__ void walk_corners_half(const K2PParams& p, const Intr
   const double2 missing = make_double2(nan(""), nan(""));
   auto obs_at = [&](int n) { return n < N ? ob[(size_t)n * kTile] : missing; };
   auto corner = [&](int n) { return n < N ? n : N - 1; };
+  // three observations in flight (the full walk keeps two): every warp of the GPU enters the tail round
+  // at the same moment with cold loads, and a half unit has only ~18 corners to amortise them over
   double2 o0 = obs_at(n0);
   double2 o1 = obs_at(n0 + 1);
+  double2 o2 = obs_at(n0 + 2);
   double iz_next = inverse_depth(sR, s_obj[3 * corner(n0)], s_obj[3 * corner(n0) + 1], s_obj[3 * corner(n0) + 2]);
 #pragma unroll 1
   for (int i = 0; i < Nh; ++i) {
     const int n = corner(n0 + i), nn = corner(n0 + i + 1);
     const double2 cur = o0;
     o0 = o1;
-    o1 = obs_at(n0 + i + 2);
+    o1 = o2;
+    o2 = obs_at(n0 + i + 3);
     const double iz = iz_next;
     iz_next = inverse_depth(sR, s_obj[3 * nn], s_obj[3 * nn + 1], s_obj[3 * nn + 2]);
     Proj pr;
@@ -491,6 +494,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
     double* uw = s_Uw + warp * kAcc;
     if (live) {
       const long long f = p.perm[tile * kTile + lane];
+      const double2* ob = p.obs + ((size_t)(tile * C + c) * N) * kTile + lane;
+      const double2 o0 = ob[0];                       // in flight during the pose loads and the Rodrigues work
+      const double2 o1 = N > 1 ? ob[kTile] : o0;
       const bool fvalid = f >= 0;
       {
         double pose[6];
@@ -506,13 +512,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
         for (int i = 0; i < 3; ++i) sR[(9 + i) * 32] = tcf[i] + cam.t[i];
       }
       __syncwarp();
-      const double2* ob = p.obs + ((size_t)(tile * C + c) * N) * kTile + lane;
       double* h = p.H + ((size_t)(tile * C + c) * kHandoff) * kTile + lane;
       double acc[kAcc];
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
       const IntrReg in{opaque(cam.fx), opaque(cam.fy), opaque(cam.cx), opaque(cam.cy), opaque(cam.k1), opaque(cam.k2)};
-      walk_corners<kLoss>(p, in, sR, ob, s_obj, acc, cost_acc, sumsq_acc, cnt_acc);
+      walk_corners<kLoss>(p, in, sR, ob, o0, o1, s_obj, acc, cost_acc, sumsq_acc, cnt_acc);
       uw[lane] = lane_transpose_sum32<0>(acc, lane);
       uw[32 + lane] = lane_transpose_sum32<32>(acc, lane);
       uw[64 + lane] = lane_transpose_sum32<64>(acc, lane);
