@@ -1,0 +1,228 @@
+// EXPERIMENT harness (k2_producer_ws.cuh against the library's K2p; scripts/experiments/README.md).
+// Stand-alone timing harness for the K2p producer kernel (k2_producer.cuh; the row-split and
+// software-pipelined variants it was used to reject are in the history, results in profiles/) on a
+// synthetic 6-camera x 50k-frame x 35-corner scene with 20 % missing views: reports ms per launch
+// and the implied FP64-pipe utilisation, and cross-checks the variants against each other.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../include -I../../multicam_calibration_b200/csrc \
+//        -o k2p_variants k2p_variants.cu
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "k2_producer_ws.cuh"
+
+namespace mcba {
+
+void set_error(const std::string&) {}
+}
+using namespace mcba;
+
+static void h_rodrigues(const double r[3], double R[9]) {
+  double th = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  double inv = th == 0 ? 1.0 : 1.0 / th, kx = r[0] * inv, ky = r[1] * inv, kz = r[2] * inv;
+  double s = std::sin(th), c = std::cos(th), oc = 1 - c, n2 = kx * kx + ky * ky + kz * kz;
+  R[0] = 1 + oc * (kx * kx - n2); R[1] = -s * kz + oc * kx * ky; R[2] = s * ky + oc * kx * kz;
+  R[3] = s * kz + oc * kx * ky; R[4] = 1 + oc * (ky * ky - n2); R[5] = -s * kx + oc * ky * kz;
+  R[6] = -s * ky + oc * kx * kz; R[7] = s * kx + oc * ky * kz; R[8] = 1 + oc * (kz * kz - n2);
+}
+
+template <int kLoss, int kWarps>
+float run_variant(const char* name, K2PParams p, int grid, std::vector<double>& H_out, std::vector<double>& U_out,
+                  size_t Hn, size_t Un, double n_obs) {
+  size_t smem = k2p_smem(p.C, p.N, kWarps);
+  cudaFuncSetAttribute(k2p_kernel<kLoss, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, k2p_kernel<kLoss, kWarps>);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e9f, sum = 0;
+  const int reps = 6;
+  for (int r = 0; r < reps + 2; ++r) {
+    cudaEventRecord(e0);
+    k2p_kernel<kLoss, kWarps><<<grid, kWarps * 32, smem>>>(p);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r >= 2) { best = ms < best ? ms : best; sum += ms; }
+  }
+  cudaError_t err = cudaGetLastError();
+  H_out.resize(Hn);
+  U_out.resize(Un);
+  cudaMemcpy(H_out.data(), p.H, Hn * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(U_out.data(), p.partU, Un * 8, cudaMemcpyDeviceToHost);
+  printf("%-34s regs %3d  spill? lmem %4zu B  grid %d x %d thr: best %.3f ms avg %.3f ms  -> %.2f Gobs/s  (%s)\n", name,
+         fa.numRegs, fa.localSizeBytes, grid, kWarps * 32, best, sum / reps, n_obs / best * 1e-6,
+         err == cudaSuccess ? "ok" : cudaGetErrorString(err));
+  return best;
+}
+
+template <int kLoss>
+float run_ws(const char* name, K2PWsParams p, int grid, std::vector<double>& H_out, std::vector<double>& U_out, size_t Hn,
+             size_t Un, double n_obs) {
+  size_t smem = k2p_ws_smem(p.C, p.N);
+  cudaFuncSetAttribute(k2p_ws_kernel<kLoss>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, k2p_ws_kernel<kLoss>);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e9f, sum = 0;
+  const int reps = 6;
+  for (int r = 0; r < reps + 2; ++r) {
+    cudaEventRecord(e0);
+    k2p_ws_kernel<kLoss><<<grid, kWsThreads, smem>>>(p);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r >= 2) { best = ms < best ? ms : best; sum += ms; }
+  }
+  cudaError_t err = cudaGetLastError();
+  H_out.resize(Hn);
+  U_out.resize(Un);
+  cudaMemcpy(H_out.data(), p.H, Hn * 8, cudaMemcpyDeviceToHost);
+  cudaMemcpy(U_out.data(), p.partU, Un * 8, cudaMemcpyDeviceToHost);
+  printf("%-34s regs %3d  lmem %4zu B  smem %zu  grid %d x %d thr: best %.3f ms avg %.3f ms  -> %.2f Gobs/s  (%s)\n", name,
+         fa.numRegs, fa.localSizeBytes, smem, grid, kWsThreads, best, sum / reps, n_obs / best * 1e-6,
+         err == cudaSuccess ? "ok" : cudaGetErrorString(err));
+  return best;
+}
+
+int main(int argc, char** argv) {
+  const int C = 6, N = 35;
+  const long long F = argc > 1 ? atoll(argv[1]) : 50000;
+  const long long nTiles = (F + 31) / 32;
+  std::mt19937_64 rng(0);
+  std::normal_distribution<double> nrm(0, 1);
+  std::uniform_real_distribution<double> uni(0, 1);
+  std::vector<double> obj(3 * N);
+  for (int i = 0; i < 5; ++i) for (int j = 0; j < 7; ++j) { int n = i * 7 + j; obj[3 * n] = j * 12.5; obj[3 * n + 1] = i * 12.5; obj[3 * n + 2] = 0; }
+  std::vector<CamConst> cams(32);
+  std::vector<double> x(12 * C + 6 * F);
+  for (int c = 0; c < C; ++c) {
+    CamConst& k = cams[c];
+    k.fx = 1200 + 20 * nrm(rng); k.fy = 1200 + 20 * nrm(rng); k.cx = 640 + 5 * nrm(rng); k.cy = 512 + 5 * nrm(rng);
+    k.k1 = -0.1 + 0.02 * nrm(rng); k.k2 = 0.05 + 0.01 * nrm(rng);
+    double r[3] = {0.3 * nrm(rng), 0.3 * nrm(rng), 0.3 * nrm(rng)};
+    h_rodrigues(r, k.R);
+    k.t[0] = 10 * nrm(rng); k.t[1] = 10 * nrm(rng); k.t[2] = 600 + 20 * nrm(rng);
+    for (int i = 0; i < 9; ++i) { k.Jl[i] = 0; k.tJ[i] = 0; }
+    double* xc = &x[12 * c];
+    xc[0] = k.fx; xc[1] = k.fy; xc[2] = k.cx; xc[3] = k.cy; xc[4] = k.k1; xc[5] = k.k2;
+    for (int i = 0; i < 3; ++i) { xc[6 + i] = r[i]; xc[9 + i] = k.t[i]; }
+  }
+  // tiled observations [tile][c][n][lane] double2, NaN padded
+  const size_t nObsSlots = (size_t)nTiles * C * N * 32;
+  std::vector<double> obs(2 * nObsSlots, NAN);
+  double n_obs = 0;
+  for (long long f = 0; f < F; ++f) {
+    double* pz = &x[12 * C + 6 * f];
+    for (int i = 0; i < 3; ++i) { pz[i] = 0.6 * nrm(rng); pz[3 + i] = 60 * nrm(rng); }
+    double Rp[9];
+    h_rodrigues(pz, Rp);
+    for (int c = 0; c < C; ++c) {
+      if (uni(rng) < 0.2) continue;
+      const CamConst& k = cams[c];
+      for (int n = 0; n < N; ++n) {
+        double w[3], q[3];
+        for (int i = 0; i < 3; ++i) w[i] = Rp[3 * i] * obj[3 * n] + Rp[3 * i + 1] * obj[3 * n + 1] + Rp[3 * i + 2] * obj[3 * n + 2] + pz[3 + i];
+        for (int i = 0; i < 3; ++i) q[i] = k.R[3 * i] * w[0] + k.R[3 * i + 1] * w[1] + k.R[3 * i + 2] * w[2] + k.t[i];
+        double xx = q[0] / q[2], yy = q[1] / q[2], r2 = xx * xx + yy * yy, d = 1 + k.k1 * r2 + k.k2 * r2 * r2;
+        size_t slot = (((size_t)(f / 32) * C + c) * N + n) * 32 + (f % 32);
+        obs[2 * slot] = k.fx * xx * d + k.cx + 0.5 * nrm(rng);
+        obs[2 * slot + 1] = k.fy * yy * d + k.cy + 0.5 * nrm(rng);
+        n_obs += 1;
+      }
+    }
+  }
+  // perturb the parameters a little so residuals are not just noise
+  for (auto& v : x) v *= 1.0 + 1e-4 * nrm(rng);
+  printf("scene: C=%d F=%lld N=%d observations=%.0f\n", C, F, N, n_obs);
+
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, 0);
+  const int grid = prop.multiProcessorCount;
+  double *d_obs, *d_obj, *d_x, *d_H, *d_partU, *d_partS;
+  const size_t Hn = (size_t)nTiles * C * kHandoff * 32, Un = (size_t)grid * C * kAcc;
+  cudaMalloc(&d_obs, obs.size() * 8); cudaMalloc(&d_obj, obj.size() * 8); cudaMalloc(&d_x, x.size() * 8);
+  cudaMalloc(&d_H, Hn * 8); cudaMalloc(&d_partU, Un * 8); cudaMalloc(&d_partS, (size_t)grid * kRsNum * 8);
+  cudaMemcpy(d_obs, obs.data(), obs.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_obj, obj.data(), obj.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_x, x.data(), x.size() * 8, cudaMemcpyHostToDevice);
+  CamConst* d_cams;
+  cudaMalloc(&d_cams, sizeof(CamConst) * 32);
+  cudaMemcpy(d_cams, cams.data(), sizeof(CamConst) * 32, cudaMemcpyHostToDevice);
+  cudaMemset(d_H, 0, Hn * 8);
+
+  // identity frame order, every (tile, camera) unit live, groups of 8 / 4 warps
+  std::vector<int> perm(nTiles * 32), units((size_t)C * nTiles), ucount(128, 0);
+  for (long long i = 0; i < nTiles * 32; ++i) perm[i] = i < F ? (int)i : -1;
+  for (int c = 0; c < C; ++c) { for (long long t = 0; t < nTiles; ++t) units[(size_t)c * nTiles + t] = (int)t; ucount[c] = (int)nTiles; }
+  int *d_perm, *d_units, *d_ucount;
+  cudaMalloc(&d_perm, perm.size() * 4); cudaMalloc(&d_units, units.size() * 4); cudaMalloc(&d_ucount, 128 * 4);
+  cudaMemcpy(d_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(d_units, units.data(), units.size() * 4, cudaMemcpyHostToDevice);
+  auto set_groups = [&](int warps) {
+    int acc = 0;
+    for (int c = 0; c < C; ++c) { ucount[32 + c] = acc; acc += (int)((nTiles + warps - 1) / warps); }
+    ucount[32 + C] = acc;
+    cudaMemcpy(d_ucount, ucount.data(), 128 * 4, cudaMemcpyHostToDevice);
+  };
+  K2PParams p;
+  p.perm = d_perm; p.units = d_units; p.unit_count = d_ucount; p.gprefix = d_ucount + 32;
+  p.C = C; p.N = N; p.F = F; p.nTiles = nTiles;
+  p.obs = reinterpret_cast<const double2*>(d_obs); p.obj = d_obj; p.x = d_x; p.cams = d_cams; p.inv_c = 1.0; p.c2 = 1.0;
+  p.H = d_H; p.partU = d_partU; p.partS = d_partS;
+
+  std::vector<double> H0, U0, H1, U1;
+  auto usum = [&](const std::vector<double>& U) {   // sum partials over CTAs -> C*96
+    std::vector<double> s(C * kAcc, 0.0);
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < C * kAcc; ++i) s[i] += U[(size_t)b * C * kAcc + i];
+    return s;
+  };
+  auto cmp = [&](const char* what, const std::vector<double>& a, const std::vector<double>& b) {
+    double mx = 0, ref = 0;
+    for (size_t i = 0; i < a.size(); ++i) { mx = fmax(mx, fabs(a[i] - b[i])); ref = fmax(ref, fabs(a[i])); }
+    printf("    %s: max |diff| %.3e  (max |ref| %.3e, rel %.2e)\n", what, mx, ref, mx / ref);
+  };
+  set_groups(8);
+  run_variant<kLossSoftL1, 8>("soft_l1, 8 warps", p, grid, H0, U0, Hn, Un, n_obs);
+  {
+    K2PWsParams pw;
+    static_cast<K2PParams&>(pw) = p;
+    cudaMalloc(&pw.partW, (size_t)grid * kWsTriples * C * kAcc * 8);
+    std::vector<double> Hw, Uw, S0((size_t)grid * kRsNum), Sw((size_t)grid * kRsNum);
+    cudaMemcpy(S0.data(), p.partS, S0.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemset(d_H, 0, Hn * 8);
+    cudaMemset(d_partU, 0xff, Un * 8);
+    run_ws<kLossSoftL1>("soft_l1, warp-specialised", pw, grid, Hw, Uw, Hn, Un, n_obs);
+    cudaMemcpy(Sw.data(), p.partS, Sw.size() * 8, cudaMemcpyDeviceToHost);
+    size_t nbits = 0;
+    for (size_t i = 0; i < Hn; ++i) nbits += memcmp(&Hw[i], &H0[i], 8) != 0;
+    printf("    H  warp-specialised vs 8 warps: %zu of %zu doubles differ bitwise\n", nbits, Hn);
+    cmp("H  warp-specialised vs 8 warps", H0, Hw);
+    cmp("U  warp-specialised vs 8 warps", usum(U0), usum(Uw));
+    double s0[3] = {0, 0, 0}, sw[3] = {0, 0, 0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 3; ++i) { s0[i] += S0[(size_t)b * kRsNum + i]; sw[i] += Sw[(size_t)b * kRsNum + i]; }
+    printf("    scalars (cost, sumsq, count): 8 warps %.12e %.12e %.0f | ws %.12e %.12e %.0f\n", s0[0], s0[1], s0[2], sw[0], sw[1], sw[2]);
+    cudaMemset(d_H, 0, Hn * 8);
+  }
+  run_variant<kLossSoftL1 | kLossIrls, 8>("soft_l1 IRLS weights, 8 warps", p, grid, H1, U1, Hn, Un, n_obs);
+  run_variant<kLossLinear, 8>("linear, 8 warps", p, grid, H1, U1, Hn, Un, n_obs);
+  set_groups(4);
+  run_variant<kLossSoftL1, 4>("soft_l1, 4 warps", p, grid, H1, U1, Hn, Un, n_obs);
+  {
+    double hs = 0, us = 0;
+    for (double v : H0) hs += fabs(v);
+    for (double v : usum(U0)) us += fabs(v);
+    printf("checksum (8 warps, soft_l1): sum|H| %.15e  sum|U| %.15e  (variant %d)\n", hs, us, MCBA_K2P_VARIANT);
+  }
+  cmp("H  4 warps vs 8 warps", H0, H1);
+  cmp("U  4 warps vs 8 warps", usum(U0), usum(U1));
+  return 0;
+}
