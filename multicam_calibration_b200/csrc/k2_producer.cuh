@@ -87,14 +87,14 @@ __device__ __forceinline__ double lane_transpose_sum32(const double (&v)[kAcc], 
   return w[0];
 }
 
-// 1/sqrt(t) for t >= 1: MUFU.RSQ64H seed, one cubic and one quadratic correction.
+// 1/sqrt(t) for t >= 1: MUFU.RSQ64H seed (relative error <= 1e-6) and ONE cubic correction
+// y (1 + e/2 + 3 e^2/8): max 1.01 ulp on B200 (scripts/ubench/seed_accuracy.cu); the quadratic step that
+// followed it until round 2 cost four dependent FP64 instructions per weight and measured 1.48 ulp.
 __device__ __forceinline__ double fast_rsqrt(double t) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(t));
-  double e = fma(-t, y * y, 1.0);
-  y = fma(y * e, fma(0.375, e, 0.5), y);
-  e = fma(-t, y * y, 1.0);
-  return fma(0.5 * y, e, y);
+  const double e = fma(-t, y * y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
 // Robust weights of one scalar residual (see robust_weights in mcba_math.cuh), branch-free on

@@ -9,6 +9,7 @@
 // other, so the host memcpy (and the page faults of a fresh destination) run kWorkers wide and
 // overlap the DMA.  A source / destination that is already pinned goes down in one async copy.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -19,8 +20,19 @@
 namespace mcba {
 namespace {
 
-constexpr int kWorkers = 8;
-constexpr size_t kChunk = 4u << 20;   // bytes per bounce buffer
+constexpr int kMaxWorkers = 32;
+constexpr size_t kMaxChunk = 8u << 20;   // bytes per bounce buffer (allocation size)
+
+// Workers and chunk size in use: tuned on the B200 box (scripts/transfer_timing.py), overridable for
+// such sweeps through MCBA_XFER_WORKERS / MCBA_XFER_CHUNK_KB (read once).
+int env_int(const char* name, int fallback, int lo, int hi) {
+  const char* v = getenv(name);
+  if (!v) return fallback;
+  const int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+const int kWorkers = env_int("MCBA_XFER_WORKERS", 8, 1, kMaxWorkers);
+const size_t kChunk = (size_t)env_int("MCBA_XFER_CHUNK_KB", 4096, 64, (int)(kMaxChunk >> 10)) << 10;
 
 struct Lane {
   unsigned char* buf[2] = {nullptr, nullptr};
@@ -30,7 +42,7 @@ struct Lane {
 
 struct Staging {
   int device = -1;
-  Lane lanes[kWorkers];
+  Lane lanes[kMaxWorkers];
   cudaEvent_t ready = nullptr;   // caller's stream -> worker streams
 };
 
@@ -48,7 +60,8 @@ int ensure_staging(int device, Staging** out) {
   Staging& g_stage = g_stages[device];
   *out = &g_stage;
   if (g_stage.device == device) return MCBA_OK;
-  for (Lane& l : g_stage.lanes) {
+  for (int w = 0; w < kWorkers; ++w) {
+    Lane& l = g_stage.lanes[w];
     for (int b = 0; b < 2; ++b) {
       MCBA_CUDA(cudaHostAlloc((void**)&l.buf[b], kChunk, cudaHostAllocDefault));
       MCBA_CUDA(cudaEventCreateWithFlags(&l.done[b], cudaEventDisableTiming));
