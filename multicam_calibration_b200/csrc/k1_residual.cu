@@ -127,12 +127,16 @@ __global__ void group_prefix_kernel(const int* __restrict__ count, int C, int wa
 }
 
 // one CTA per (tile, camera) unit: coalesced row loads -> shared -> coalesced [n][lane] stores
+// Also counts the finite scalars it moves (n_scalars, zeroed by the caller): the residual count K2p reports
+// with every evaluation without counting again.
 __global__ void __launch_bounds__(256) tile_observations_kernel(const double2* __restrict__ ref,
                                                                 double2* __restrict__ tiled,
                                                                 const int* __restrict__ perm, int C, long long F,
-                                                                int N, long long nUnits) {
+                                                                int N, long long nUnits,
+                                                                unsigned long long* __restrict__ n_scalars) {
   extern __shared__ double2 s_rows[];   // [32][N + 1]
   const int ldr = N + 1;
+  unsigned int finite = 0;
   for (long long unit = blockIdx.x; unit < nUnits; unit += gridDim.x) {
     const long long tile = unit / C;
     const int c = (int)(unit % C);
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(256) tile_observations_kernel(const double2* _
       const int f = perm[tile * kTile + r];
       double2 v = make_double2(nan(""), nan(""));
       if (f >= 0) v = ref[((long long)c * F + f) * N + n];
+      finite += (v.x == v.x ? 1u : 0u) + (v.y == v.y ? 1u : 0u);
       s_rows[r * ldr + n] = v;
     }
     __syncthreads();
@@ -148,6 +153,9 @@ __global__ void __launch_bounds__(256) tile_observations_kernel(const double2* _
     for (int i = threadIdx.x; i < kTile * N; i += blockDim.x) out[i] = s_rows[(i % kTile) * ldr + i / kTile];
     __syncthreads();
   }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) finite += __shfl_xor_sync(0xffffffffu, finite, off);
+  if ((threadIdx.x & 31) == 0 && finite) atomicAdd(n_scalars, (unsigned long long)finite);
 }
 
 // finite scalars per group of 32 consecutive (c,f,n) slots (one warp per group) + number of
@@ -203,8 +211,10 @@ int launch_tile_observations(mcba_handle* h) {
   tile_active_kernel<<<blocks, 256, 0, h->stream>>>(h->d_mask, h->d_perm, L.F, L.nTiles, h->d_active);
   const long long units = L.nTiles * L.C;
   const int grid = (int)(units < 148 * 8 ? units : 148 * 8);
+  unsigned long long* n_scalars = reinterpret_cast<unsigned long long*>(h->d_unit_count + 96);
+  MCBA_CUDA(cudaMemsetAsync(n_scalars, 0, sizeof(unsigned long long), h->stream));
   tile_observations_kernel<<<grid, 256, sizeof(double2) * kTile * (L.N + 1), h->stream>>>(
-      reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obs_tiled, h->d_perm, L.C, L.F, L.N, units);
+      reinterpret_cast<const double2*>(h->d_obs_ref), h->d_obs_tiled, h->d_perm, L.C, L.F, L.N, units, n_scalars);
   build_units_kernel<<<L.C, 256, 0, h->stream>>>(h->d_active, L.nTiles, h->d_units, h->d_unit_count);
   group_prefix_kernel<<<1, 32, 0, h->stream>>>(h->d_unit_count, L.C, h->prod_warps, h->d_unit_count + 32);
   // dead units are never written by K2p: their hand-off stays zero

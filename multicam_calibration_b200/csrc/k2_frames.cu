@@ -414,6 +414,7 @@ int launch_k2_producer(mcba_handle* h, const double* x, int loss, double f_scale
   p.H = h->d_H;
   p.partU = h->d_partU;
   p.partS = h->d_partS;
+  p.n_scalars = reinterpret_cast<const unsigned long long*>(h->d_unit_count + 96);
   if ((loss & 0xff) == kLossLinear) return launch_k2p_w<kLossLinear>(h, p);
   if (loss & kLossIrls) return launch_k2p_w<kLossSoftL1 | kLossIrls>(h, p);
   return launch_k2p_w<kLossSoftL1>(h, p);

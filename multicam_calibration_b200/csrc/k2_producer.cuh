@@ -43,6 +43,7 @@ struct K2PParams {
   double* H;                  // [tile][c][63][32]
   double* partU;              // [grid][C][kAcc]
   double* partS;              // [grid][kRsNum]
+  const unsigned long long* n_scalars;   // finite observation scalars of this rank's frames
 };
 
 template <bool IsU>
@@ -98,24 +99,33 @@ __device__ __forceinline__ double fast_rsqrt(double t) {
 }
 
 // Robust weights of one scalar residual (see robust_weights in mcba_math.cuh), branch-free on
-// the data: f == 0 for a missing scalar gives rho = 0 and a zero gradient term by itself; only
-// the Gauss-Newton weight needs the validity select.
+// the data: f == 0 for a missing scalar gives a zero gradient term by itself; only the Gauss-Newton
+// weight needs the validity select.  The cost is accumulated in the cheapest form the loss allows:
+//   soft_l1:  rho = 2 c^2 (sqrt(1 + z) - 1) with sqrt(1 + z) = t * rsqrt(t): ONE fma per scalar adds
+//             t b to the running sum; the "- 1" (every walked slot, missing ones included: they add
+//             t b = 1) and the factor 2 c^2 are applied once per thread (k2p_cost_of_thread);
+//   linear:   rho = f^2, one fma.
 template <int kLoss>
-__device__ __forceinline__ void robust_weights_t(double f, bool valid, double inv_c, double c2, double& rho,
-                                                 double& wg, double& wh) {
+__device__ __forceinline__ void robust_weights_t(double f, bool valid, double inv_c, double& cost_acc, double& wg,
+                                                 double& wh) {
   if ((kLoss & 0xff) == kLossLinear) {
-    rho = f * f;
+    cost_acc = fma(f, f, cost_acc);
     wg = 1.0;
     wh = valid ? 1.0 : 0.0;
   } else {
     const double fs = f * inv_c;
     const double t = fma(fs, fs, 1.0);
     const double b = fast_rsqrt(t);
-    rho = 2.0 * fma(t, b, -1.0) * c2;
+    cost_acc = fma(t, b, cost_acc);
     wg = b;
     const double w3 = (kLoss & kLossIrls) ? b : fmax(b * b * b, 2.220446049250313e-16);
     wh = valid ? w3 : 0.0;
   }
+}
+// sum of rho over the slots a thread walked, from its running sum and the number of scalar slots
+template <int kLoss>
+__device__ __forceinline__ double k2p_cost_of_thread(double cost_acc, double slots, double c2) {
+  return (kLoss & 0xff) == kLossLinear ? cost_acc : 2.0 * c2 * (cost_acc - slots);
 }
 
 #ifndef MCBA_K2P_LAUNDER
@@ -226,23 +236,19 @@ __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& 
     {
       const bool hu = cur.x == cur.x;
       const double fu = hu ? cur.x - pr.pu : 0.0;
-      double rho, wg, wh, au[10];
-      robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wh);
+      double wg, wh, au[10];
+      robust_weights_t<kLoss>(fu, hu, p.inv_c, cost_acc, wg, wh);
       jac_row<true>(cam, pr, au);
-      cost_acc += rho;
       sumsq_acc = fma(fu, fu, sumsq_acc);
-      cnt_acc += hu ? 1.0 : 0.0;
       accumulate_row<true>(acc, au, wh, -wg * fu);
     }
     {
       const bool hv = cur.y == cur.y;
       const double fv = hv ? cur.y - pr.pv : 0.0;
-      double rho, wg, wh, av[10];
-      robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wh);
+      double wg, wh, av[10];
+      robust_weights_t<kLoss>(fv, hv, p.inv_c, cost_acc, wg, wh);
       jac_row<false>(cam, pr, av);
-      cost_acc += rho;
       sumsq_acc = fma(fv, fv, sumsq_acc);
-      cnt_acc += hv ? 1.0 : 0.0;
       accumulate_row<false>(acc, av, wh, -wg * fv);
     }
   }
@@ -295,23 +301,19 @@ __device__ __forceinline__ void walk_corners(const K2PParams& p, const IntrReg& 
     {
       const bool hu = cur.x == cur.x;
       const double fu = hu ? cur.x - pr.pu : 0.0;
-      double rho, wg, wh, au[10];
-      robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wh);
+      double wg, wh, au[10];
+      robust_weights_t<kLoss>(fu, hu, p.inv_c, cost_acc, wg, wh);
       jac_row<true>(cam, pr, au);
-      cost_acc += rho;
       sumsq_acc = fma(fu, fu, sumsq_acc);
-      cnt_acc += hu ? 1.0 : 0.0;
       accumulate_row<true>(acc, au, wh, -wg * fu);
     }
     {
       const bool hv = cur.y == cur.y;
       const double fv = hv ? cur.y - pr.pv : 0.0;
-      double rho, wg, wh, av[10];
-      robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wh);
+      double wg, wh, av[10];
+      robust_weights_t<kLoss>(fv, hv, p.inv_c, cost_acc, wg, wh);
       jac_row<false>(cam, pr, av);
-      cost_acc += rho;
       sumsq_acc = fma(fv, fv, sumsq_acc);
-      cnt_acc += hv ? 1.0 : 0.0;
       accumulate_row<false>(acc, av, wh, -wg * fv);
     }
   }
@@ -329,22 +331,18 @@ __device__ __forceinline__ void corner_front(const K2PParams& p, const IntrReg& 
   {
     const bool hu = cur.x == cur.x;
     const double fu = hu ? cur.x - pr.pu : 0.0;
-    double rho, wg;
-    robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wu.wh);
+    double wg;
+    robust_weights_t<kLoss>(fu, hu, p.inv_c, cost_acc, wg, wu.wh);
     wu.gf = -wg * fu;
-    cost_acc += rho;
     sumsq_acc = fma(fu, fu, sumsq_acc);
-    cnt_acc += hu ? 1.0 : 0.0;
   }
   {
     const bool hv = cur.y == cur.y;
     const double fv = hv ? cur.y - pr.pv : 0.0;
-    double rho, wg;
-    robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wv.wh);
+    double wg;
+    robust_weights_t<kLoss>(fv, hv, p.inv_c, cost_acc, wg, wv.wh);
     wv.gf = -wg * fv;
-    cost_acc += rho;
     sumsq_acc = fma(fv, fv, sumsq_acc);
-    cnt_acc += hv ? 1.0 : 0.0;
   }
 }
 template <int kLoss>
@@ -410,23 +408,19 @@ __device__ __forceinline__ void walk_corners_half(const K2PParams& p, const Intr
     {
       const bool hu = cur.x == cur.x;
       const double fu = hu ? cur.x - pr.pu : 0.0;
-      double rho, wg, wh, au[10];
-      robust_weights_t<kLoss>(fu, hu, p.inv_c, p.c2, rho, wg, wh);
+      double wg, wh, au[10];
+      robust_weights_t<kLoss>(fu, hu, p.inv_c, cost_acc, wg, wh);
       jac_row<true>(cam, pr, au);
-      cost_acc += rho;
       sumsq_acc = fma(fu, fu, sumsq_acc);
-      cnt_acc += hu ? 1.0 : 0.0;
       accumulate_row<true>(acc, au, wh, -wg * fu);
     }
     {
       const bool hv = cur.y == cur.y;
       const double fv = hv ? cur.y - pr.pv : 0.0;
-      double rho, wg, wh, av[10];
-      robust_weights_t<kLoss>(fv, hv, p.inv_c, p.c2, rho, wg, wh);
+      double wg, wh, av[10];
+      robust_weights_t<kLoss>(fv, hv, p.inv_c, cost_acc, wg, wh);
       jac_row<false>(cam, pr, av);
-      cost_acc += rho;
       sumsq_acc = fma(fv, fv, sumsq_acc);
-      cnt_acc += hv ? 1.0 : 0.0;
       accumulate_row<false>(acc, av, wh, -wg * fv);
     }
   }
@@ -464,7 +458,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
   }
   for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_obj[i] = p.obj[i];
   for (int i = threadIdx.x; i < C * kAcc; i += blockDim.x) s_U[i] = 0.0;
-  double cost_acc = 0.0, sumsq_acc = 0.0, cnt_acc = 0.0;
+  double cost_acc = 0.0, sumsq_acc = 0.0, cnt_acc = 0.0;   // cnt_acc: scalar slots this thread walked (k2p_cost_of_thread)
   double* sR = s_R + (size_t)warp * 12 * 32 + lane;
   __syncthreads();
 
@@ -518,6 +512,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
       const IntrReg in{opaque(cam.fx), opaque(cam.fy), opaque(cam.cx), opaque(cam.cy), opaque(cam.k1), opaque(cam.k2)};
       walk_corners<kLoss>(p, in, sR, ob, o0, o1, s_obj, acc, cost_acc, sumsq_acc, cnt_acc);
+      cnt_acc += 2.0 * (MCBA_K2P_VARIANT == 2 ? N + 1 : N);
       uw[lane] = lane_transpose_sum32<0>(acc, lane);
       uw[32 + lane] = lane_transpose_sum32<32>(acc, lane);
       uw[64 + lane] = lane_transpose_sum32<64>(acc, lane);
@@ -580,6 +575,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
       const IntrReg in{opaque(cam.fx), opaque(cam.fy), opaque(cam.cx), opaque(cam.cy), opaque(cam.k1), opaque(cam.k2)};
       walk_corners_half<kLoss>(p, in, sR, ob, s_obj, lane, acc, cost_acc, sumsq_acc, cnt_acc);
+      cnt_acc += 2.0 * ((N + 1) >> 1);
       uw[lane] = lane_transpose_sum32<0>(acc, lane);
       uw[32 + lane] = lane_transpose_sum32<32>(acc, lane);
       uw[64 + lane] = lane_transpose_sum32<64>(acc, lane);
@@ -613,31 +609,31 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k2p_kernel(const K2PParams p) 
   // ---------------- CTA epilogue: partial sums ----------------
   double* pu = p.partU + (size_t)blockIdx.x * C * kAcc;
   for (int i = threadIdx.x; i < C * kAcc; i += blockDim.x) pu[i] = s_U[i];
+  cost_acc = k2p_cost_of_thread<kLoss>(cost_acc, cnt_acc, p.c2);
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     cost_acc += __shfl_xor_sync(0xffffffffu, cost_acc, off);
     sumsq_acc += __shfl_xor_sync(0xffffffffu, sumsq_acc, off);
-    cnt_acc += __shfl_xor_sync(0xffffffffu, cnt_acc, off);
   }
   __syncthreads();
   double* s_red = s_Uw;
   if (lane == 0) {
     s_red[warp * 4 + 0] = cost_acc;
     s_red[warp * 4 + 1] = sumsq_acc;
-    s_red[warp * 4 + 2] = cnt_acc;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double a = 0, b = 0, cn = 0;
+    double a = 0, b = 0;
     for (int w = 0; w < kWarps; ++w) {
       a += s_red[w * 4];
       b += s_red[w * 4 + 1];
-      cn += s_red[w * 4 + 2];
     }
     double* ps = p.partS + (size_t)blockIdx.x * kRsNum;
     ps[kRsCost] = 0.5 * a;
     ps[kRsSumSq] = b;
-    ps[kRsCount] = cn;
+    // the number of finite scalars does not change between evaluations: counted once when the observations
+    // were tiled (tile_observations_kernel), reported by CTA 0
+    ps[kRsCount] = blockIdx.x == 0 ? (double)*p.n_scalars : 0.0;
     ps[kRsGmaxPose] = 0.0;   // pose gradients are K2c's (partG)
   }
 }

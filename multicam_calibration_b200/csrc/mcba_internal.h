@@ -51,7 +51,7 @@ struct mcba_handle {
   unsigned int* d_mask = nullptr;    // [2 Fpad] ~visibility mask per frame | sort scratch
   unsigned int* d_active = nullptr;  // [nTiles] cameras with at least one observation in the tile
   int* d_units = nullptr;            // [C][nTiles] live tiles per camera, compacted
-  int* d_unit_count = nullptr;       // [0..C) live units per camera | [32..32+C] group prefix for K2p
+  int* d_unit_count = nullptr;       // [0..C) live units per camera | [32..32+C] group prefix for K2p | [96..97] finite scalars (u64, K2p's count)
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   long long* d_row_off = nullptr;  // exclusive scan of finite scalars per group of 32 (c,f,n) slots

@@ -178,6 +178,10 @@ int main(int argc, char** argv) {
   p.C = C; p.N = N; p.F = F; p.nTiles = nTiles;
   p.obs = reinterpret_cast<const double2*>(d_obs); p.obj = d_obj; p.x = d_x; p.cams = d_cams; p.inv_c = 1.0; p.c2 = 1.0;
   p.H = d_H; p.partU = d_partU; p.partS = d_partS;
+  unsigned long long* d_nsc;
+  cudaMalloc(&d_nsc, 8);
+  { unsigned long long v = (unsigned long long)(2 * n_obs); cudaMemcpy(d_nsc, &v, 8, cudaMemcpyHostToDevice); }
+  p.n_scalars = d_nsc;
 
   std::vector<double> H0, U0, H1, U1;
   auto usum = [&](const std::vector<double>& U) {   // sum partials over CTAs -> C*96
