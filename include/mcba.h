@@ -125,7 +125,12 @@ int mcba_cost(mcba_handle* h, const double* d_x, int loss, double f_scale, doubl
 int mcba_build_reduced(mcba_handle* h, const double* d_x, double lambda, int loss, double f_scale,
                        double* h_S, double* h_b, double* h_gcam, double* h_cost);
 /* Same, through HOST buffers end to end: uploads uvs (C,F,N,2) and x, runs the
- * pass, downloads S, b.  This is the call bench.py times as "e2e". */
+ * pass, downloads S, b.  This is the call bench.py times as "e2e".  With page-locked
+ * buffers and >= 16384 frames the observations cross PCIe in eight frame ranges, each
+ * tiled, evaluated and reduced while the next is in flight (sums over frames are added
+ * at the end); the handle is afterwards usable exactly as after
+ * mcba_set_observations + mcba_build_reduced.  MCBA_NO_HOST_PIPELINE=1 forces the
+ * single-upload path; pageable buffers always take it (staged by mcba_upload). */
 int mcba_build_reduced_host(mcba_handle* h, const double* h_uvs, const double* h_objpoints,
                             const double* h_x, double lambda, int loss, double f_scale,
                             double* h_S, double* h_b, double* h_cost);

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "mcba_internal.h"
 #include "mcba_peer.cuh"
@@ -18,6 +19,10 @@ namespace mcba {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 int solve_reduced(mcba_handle* h, double lambda);
+static void destroy_pipe(mcba_handle* h);   // chunked host path of mcba_build_reduced_host (below)
+static bool pipe_parent_is_stale(mcba_handle* h);
+static int refresh_parent_from_pipe(mcba_handle* h);
+static void pipe_forget(mcba_handle* h);
 
 // ------------------------------------------------------------------ NCCL (resolved lazily: torch already maps libnccl.so.2)
 struct NcclApi {
@@ -388,6 +393,7 @@ int mcba_create(mcba_handle** out, int C, int64_t F, int N, int device) {
 int mcba_destroy(mcba_handle* h) {
   if (!h) return MCBA_OK;
   cudaSetDevice(h->device);
+  destroy_pipe(h);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   if (h->solver) cusolverDnDestroy(h->solver);
   for (int s = 0; s < kMaxRanks; ++s) if (h->peer_mapped[s]) cudaIpcCloseMemHandle(h->peer_mapped[s]);
@@ -433,11 +439,12 @@ int mcba_synchronize(mcba_handle* h) {
 int mcba_set_observations(mcba_handle* h, const double* uvs, const double* obj, int is_device) {
   if (!h || !uvs || !obj) { set_error("mcba_set_observations: null argument"); return MCBA_ERR_ARG; }
   MCBA_CUDA(cudaSetDevice(h->device));
+  pipe_forget(h);   // new observations supersede what a pipelined host call left in its children
   const Layout& L = h->L;
   const size_t uv_bytes = sizeof(double) * (size_t)L.C * L.F * L.N * 2;
   if (is_device) {
-    MCBA_CUDA(cudaMemcpyAsync(h->d_obs_ref, uvs, uv_bytes, cudaMemcpyDeviceToDevice, h->stream));
-    MCBA_CUDA(cudaMemcpyAsync(h->d_obj, obj, sizeof(double) * 3 * L.N, cudaMemcpyDeviceToDevice, h->stream));
+    if (uvs != h->d_obs_ref) MCBA_CUDA(cudaMemcpyAsync(h->d_obs_ref, uvs, uv_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (obj != h->d_obj) MCBA_CUDA(cudaMemcpyAsync(h->d_obj, obj, sizeof(double) * 3 * L.N, cudaMemcpyDeviceToDevice, h->stream));
   } else {
     // caller-owned host memory: pinned buffers take one async copy, pageable ones (a numpy array) are
     // staged through the multi-threaded bounce buffers of mcba_upload instead of the driver's single one
@@ -458,7 +465,7 @@ int mcba_set_observations(mcba_handle* h, const double* uvs, const double* obj, 
 static int need_obs(mcba_handle* h) {
   if (!h || !h->have_obs) { set_error("observations not set (call mcba_set_observations first)"); return MCBA_ERR_STATE; }
   MCBA_CUDA(cudaSetDevice(h->device));
-  return MCBA_OK;
+  return pipe_parent_is_stale(h) ? refresh_parent_from_pipe(h) : MCBA_OK;
 }
 
 int mcba_num_residuals(mcba_handle* h, int64_t* m, int64_t* nobs) {
@@ -516,9 +523,221 @@ int mcba_build_reduced(mcba_handle* h, const double* d_x, double lambda, int los
   return MCBA_OK;
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// mcba_build_reduced_host, pipelined.  The call is bound by PCIe (168 MB of observations at BASELINE
+// configs[2] against a 0.36 ms pass), and its dependent tail -- frame masks, sort, tiling, the pass
+// itself -- only starts when the last byte has landed.  With page-locked host buffers and enough
+// frames the observations instead cross in kHostChunks frame ranges on a copy stream; every range is a
+// complete small problem of its own (a child handle: tiled, evaluated and reduced while the next range
+// is in flight), and S, b, the camera gradient and the scalars of the ranges, all sums over frames,
+// are added at the end (the additivity tests/test_gpu_parity.py checks for shards).  Afterwards
+// the parent's own copy of the observations is refreshed from the children asynchronously, so the
+// handle is left as after mcba_set_observations.  MCBA_NO_HOST_PIPELINE=1 forces the plain path.
+namespace mcba {
+constexpr int kHostChunks = 8;
+constexpr long long kHostPipeMinFrames = 16384;
+
+struct HostPipe {
+  std::vector<mcba_handle*> kids;
+  std::vector<long long> f0;
+  std::vector<cudaEvent_t> landed, done;   // per range: copy finished / evaluation finished (timed: MCBA_PIPE_TRACE)
+  cudaEvent_t t0 = nullptr, params = nullptr;
+  double* d_x = nullptr;              // staging: [x (12C + 6F) | objpoints (3N)]
+  cudaStream_t copy = nullptr;
+  cudaEvent_t begin = nullptr;
+  const double** d_table = nullptr;   // the children's packed systems (device pointers, fixed)
+  bool parent_stale = false;          // the last call's observations are in the children only
+  double lambda = 0.0, f_scale = 1.0; // ... and so is its evaluation (re-run on the parent when it is needed)
+  int loss = 0;
+};
+
+static void destroy_pipe(mcba_handle* h) {
+  HostPipe* P = h->pipe;
+  if (!P) return;
+  for (mcba_handle* k : P->kids) mcba_destroy(k);
+  for (cudaEvent_t e : P->landed) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : P->done) if (e) cudaEventDestroy(e);
+  if (P->t0) cudaEventDestroy(P->t0);
+  if (P->params) cudaEventDestroy(P->params);
+  if (P->d_x) cudaFree(P->d_x);
+  if (P->begin) cudaEventDestroy(P->begin);
+  if (P->copy) cudaStreamDestroy(P->copy);
+  if (P->d_table) cudaFree(P->d_table);
+  delete P;
+  h->pipe = nullptr;
+}
+
+static bool pipe_parent_is_stale(mcba_handle* h) { return h->pipe && h->pipe->parent_stale; }
+static void pipe_forget(mcba_handle* h) { if (h->pipe) h->pipe->parent_stale = false; }
+
+static bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_pipe(mcba_handle* h) {
+  if (h->pipe) {
+    for (mcba_handle* k : h->pipe->kids) k->stream = h->stream;   // the parent's stream may have been replaced
+    return MCBA_OK;
+  }
+  const Layout& L = h->L;
+  HostPipe* P = new HostPipe();
+  h->pipe = P;
+  const long long tiles_per_chunk = (L.nTiles + kHostChunks - 1) / kHostChunks;
+  for (int k = 0; k < kHostChunks; ++k) {
+    const long long f0 = (long long)k * tiles_per_chunk * kTile;
+    if (f0 >= L.F) break;
+    const long long fk = std::min<long long>(L.F - f0, tiles_per_chunk * kTile);
+    mcba_handle* kid = nullptr;
+    int rc = mcba_create(&kid, L.C, fk, L.N, h->device);
+    if (rc) return rc;
+    if (kid->own_stream && kid->stream) cudaStreamDestroy(kid->stream);
+    kid->stream = h->stream;
+    kid->own_stream = false;
+    P->kids.push_back(kid);
+    P->f0.push_back(f0);
+    cudaEvent_t e = nullptr;
+    MCBA_CUDA(cudaEventCreate(&e));
+    P->landed.push_back(e);
+    MCBA_CUDA(cudaEventCreate(&e));
+    P->done.push_back(e);
+  }
+  MCBA_CUDA(cudaStreamCreateWithFlags(&P->copy, cudaStreamNonBlocking));
+  MCBA_CUDA(cudaEventCreateWithFlags(&P->begin, cudaEventDisableTiming));
+  MCBA_CUDA(cudaEventCreate(&P->t0));
+  MCBA_CUDA(cudaEventCreateWithFlags(&P->params, cudaEventDisableTiming));
+  MCBA_CUDA(cudaMalloc((void**)&P->d_x, sizeof(double) * (L.nc + 6 * L.F + 3 * L.N)));
+  std::vector<const double*> table;
+  for (mcba_handle* k : P->kids) table.push_back(k->d_red);
+  MCBA_CUDA(cudaMalloc((void**)&P->d_table, sizeof(double*) * table.size()));
+  MCBA_CUDA(cudaMemcpy(P->d_table, table.data(), sizeof(double*) * table.size(), cudaMemcpyHostToDevice));
+  return MCBA_OK;
+}
+
+// out[i] = sum over the children of their packed [S | b | g | diag U | cost, sum f^2, count]
+__global__ void sum_children_kernel(const double* const* __restrict__ red, int n_kids, long long n, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < n_kids; ++k) s += red[k][i];
+    out[i] = s;
+  }
+}
+
+static int new_problem_state(mcba_handle* h) {
+  const Layout& L = h->L;
+  h->have_obs = true;
+  h->have_rows = false;
+  // a new problem: reset the running Marquardt scaling
+  MCBA_CUDA(cudaMemsetAsync(h->d_D2pose, 0, sizeof(double) * L.nTiles * 6 * kTile, h->stream));
+  MCBA_CUDA(cudaMemsetAsync(h->d_D2cam, 0, sizeof(double) * L.nc, h->stream));
+  return MCBA_OK;
+}
+
+static int build_reduced_host_pipelined(mcba_handle* h, const double* h_uvs, const double* h_obj, const double* h_x,
+                                        double lambda, int loss, double f_scale, double* h_S, double* h_b,
+                                        double* h_cost) {
+  MCBA_CUDA(cudaSetDevice(h->device));
+  int rc = ensure_pipe(h);
+  if (rc) { const std::string why = g_error; destroy_pipe(h); set_error(why); return rc; }
+  HostPipe& P = *h->pipe;
+  const Layout& L = h->L;
+  const size_t row = sizeof(double) * 2 * (size_t)L.N;           // one (camera, frame) row of corners
+  // the copy stream must not overwrite the children's buffers while the previous call's refresh of the
+  // parent still reads them (P.begin: recorded behind those copies; a no-op on the first call)
+  MCBA_CUDA(cudaStreamWaitEvent(P.copy, P.begin, 0));
+  MCBA_CUDA(cudaEventRecord(P.t0, P.copy));
+  const int n_kids = (int)P.kids.size();
+  // Parameters and board first (2.4 MB, ONE transfer each into the pipeline's own staging block: nothing else
+  // reads it, so the copy stream need not wait for the compute stream); the children take their slices from
+  // there on the device and the copy engine sees nothing but the eight large transfers afterwards.
+  MCBA_CUDA(cudaMemcpyAsync(P.d_x, h_x, sizeof(double) * (L.nc + 6 * L.F), cudaMemcpyHostToDevice, P.copy));
+  MCBA_CUDA(cudaMemcpyAsync(P.d_x + L.nc + 6 * L.F, h_obj, sizeof(double) * 3 * L.N, cudaMemcpyHostToDevice, P.copy));
+  MCBA_CUDA(cudaEventRecord(P.params, P.copy));
+  for (int k = 0; k < n_kids; ++k) {
+    mcba_handle* kid = P.kids[k];
+    const long long f0 = P.f0[k], fk = kid->L.F;
+    MCBA_CUDA(cudaMemcpy2DAsync(kid->d_obs_ref, row * fk, h_uvs + (size_t)f0 * 2 * L.N, row * L.F, row * fk, L.C,
+                                cudaMemcpyHostToDevice, P.copy));
+    MCBA_CUDA(cudaEventRecord(P.landed[k], P.copy));
+  }
+  // every range is queued on the copy engine before the first kernel is: nothing on the compute side
+  // (launch latency, a host synchronisation in a set-up step) can delay the transfers
+  MCBA_CUDA(cudaStreamWaitEvent(h->stream, P.params, 0));
+  for (int k = 0; k < n_kids; ++k) {
+    mcba_handle* kid = P.kids[k];
+    const long long f0 = P.f0[k], fk = kid->L.F;
+    MCBA_CUDA(cudaMemcpyAsync(kid->d_obj, P.d_x + L.nc + 6 * L.F, sizeof(double) * 3 * L.N, cudaMemcpyDeviceToDevice, h->stream));
+    MCBA_CUDA(cudaMemcpyAsync(kid->d_x, P.d_x, sizeof(double) * L.nc, cudaMemcpyDeviceToDevice, h->stream));
+    MCBA_CUDA(cudaMemcpyAsync(kid->d_x + L.nc, P.d_x + L.nc + 6 * f0, sizeof(double) * 6 * fk, cudaMemcpyDeviceToDevice, h->stream));
+    MCBA_CUDA(cudaStreamWaitEvent(h->stream, P.landed[k], 0));
+    if ((rc = launch_tile_observations(kid))) return rc;
+    if ((rc = new_problem_state(kid))) return rc;
+    if ((rc = evaluate(kid, kid->d_x, lambda, loss, f_scale))) return rc;
+    MCBA_CUDA(cudaEventRecord(P.done[k], h->stream));
+  }
+  // sum of the children's packed systems
+  const long long n_sum = L.offScal + 3;
+  sum_children_kernel<<<(int)((n_sum + 255) / 256), 256, 0, h->stream>>>(P.d_table, n_kids, n_sum, h->d_red);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  if (h_S) MCBA_CUDA(cudaMemcpyAsync(h_S, h->d_red + L.offS, sizeof(double) * L.nc * L.nc, cudaMemcpyDeviceToHost, h->stream));
+  if (h_b) MCBA_CUDA(cudaMemcpyAsync(h_b, h->d_red + L.offB, sizeof(double) * L.nc, cudaMemcpyDeviceToHost, h->stream));
+  if (h_cost) MCBA_CUDA(cudaMemcpyAsync(h_cost, h->d_red + L.offScal + kRsCost, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  MCBA_CUDA(cudaStreamSynchronize(h->stream));
+  if (getenv("MCBA_PIPE_TRACE")) {
+    for (int k = 0; k < n_kids; ++k) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, P.t0, P.landed[k]);
+      cudaEventElapsedTime(&b, P.t0, P.done[k]);
+      fprintf(stderr, "[mcba pipe] range %d: landed %.3f ms, evaluated %.3f ms\n", k, a, b);
+    }
+  }
+  // The observations now live in the children.  The parent's own tiled copy (what mcba_set_observations would have
+  // left) is rebuilt from them when a later call needs it (need_obs): back-to-back host-buffer calls never pay for it.
+  P.parent_stale = true;
+  P.lambda = lambda; P.loss = loss; P.f_scale = f_scale;
+  h->have_obs = true;
+  return MCBA_OK;
+}
+
+// the parent's observations, parameters and tiling from the children of the last pipelined call
+static int refresh_parent_from_pipe(mcba_handle* h) {
+  HostPipe& P = *h->pipe;
+  const Layout& L = h->L;
+  const size_t row = sizeof(double) * 2 * (size_t)L.N;
+  for (size_t k = 0; k < P.kids.size(); ++k) {
+    mcba_handle* kid = P.kids[k];
+    MCBA_CUDA(cudaMemcpy2DAsync(h->d_obs_ref + (size_t)P.f0[k] * 2 * L.N, row * L.F, kid->d_obs_ref, row * kid->L.F,
+                                row * kid->L.F, L.C, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  MCBA_CUDA(cudaMemcpyAsync(h->d_x, P.d_x, sizeof(double) * (L.nc + 6 * L.F), cudaMemcpyDeviceToDevice, h->stream));
+  MCBA_CUDA(cudaMemcpyAsync(h->d_obj, P.d_x + L.nc + 6 * L.F, sizeof(double) * 3 * L.N, cudaMemcpyDeviceToDevice, h->stream));
+  MCBA_CUDA(cudaEventRecord(P.begin, h->stream));   // the children's buffers and the staging block are free from here on
+  P.parent_stale = false;
+  int rc = launch_tile_observations(h);
+  if (rc) return rc;
+  if ((rc = new_problem_state(h))) return rc;
+  // ... and the evaluation itself (Z, L^-1, y, pose gradients of the WHOLE problem), so that mcba_solve_step /
+  // mcba_gradient find what the plain path would have left
+  return evaluate(h, h->d_x, P.lambda, P.loss, P.f_scale);
+}
+}  // namespace mcba
+
+extern "C" {
+
 int mcba_build_reduced_host(mcba_handle* h, const double* h_uvs, const double* h_obj, const double* h_x,
                             double lambda, int loss, double f_scale, double* h_S, double* h_b, double* h_cost) {
   if (!h) return MCBA_ERR_ARG;
+  if (!h_uvs || !h_obj || !h_x) { set_error("mcba_build_reduced_host: null argument"); return MCBA_ERR_ARG; }
+  if (h->L.F >= kHostPipeMinFrames && h->nranks <= 1 && !getenv("MCBA_NO_HOST_PIPELINE") && host_pointer_is_pinned(h_uvs) &&
+      host_pointer_is_pinned(h_x))
+    return build_reduced_host_pipelined(h, h_uvs, h_obj, h_x, lambda, loss, f_scale, h_S, h_b, h_cost);
   int rc = mcba_set_observations(h, h_uvs, h_obj, 0);
   if (rc) return rc;
   const long long n = h->L.nc + 6 * h->L.F;
@@ -540,6 +759,8 @@ int mcba_solve_step(mcba_handle* h, const double* d_x, double lambda, double* d_
 
 int mcba_gradient(mcba_handle* h, double* d_grad) {
   // gradient of 0.5 sum rho at the last evaluated point: [g_cam | g_pose]
+  int rc = need_obs(h);
+  if (rc) return rc;
   const Layout& L = h->L;
   MCBA_CUDA(cudaMemcpyAsync(d_grad, h->d_red + L.offG, sizeof(double) * L.nc, cudaMemcpyDeviceToDevice, h->stream));
   MCBA_CUDA(cudaMemcpyAsync(d_grad + L.nc, h->d_gpose, sizeof(double) * 6 * L.F, cudaMemcpyDeviceToDevice, h->stream));

@@ -37,8 +37,11 @@ struct Layout {
 
 }  // namespace mcba
 
+namespace mcba { struct HostPipe; }
+
 struct mcba_handle {
   mcba::Layout L;
+  mcba::HostPipe* pipe = nullptr;   // chunked upload + evaluation of mcba_build_reduced_host (mcba_api.cu), lazily built
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;

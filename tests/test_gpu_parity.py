@@ -707,3 +707,51 @@ def test_reprojection_residuals_exact_homography():
     np.testing.assert_allclose(rep, uvs, rtol=1e-11)
     err = np.linalg.norm(tr - sc.objpoints[:, :2], axis=-1)
     assert np.nanmax(err) < 5e-3 and np.all(med < 1e-3)
+
+
+def test_host_buffer_call_pipelined_equals_plain_and_leaves_the_problem_usable(monkeypatch):
+    """mcba_build_reduced_host with page-locked buffers and >= 16384 frames streams the observations in
+    frame ranges that are tiled, evaluated and reduced while the next range is in flight: S, b and the
+    cost must equal the plain path's (one upload, one evaluation) and the device-resident evaluation,
+    and the handle must be left as after mcba_set_observations."""
+    import ctypes
+    import torch
+    from multicam_calibration_b200 import _native
+    lib = _native.load()
+    sc = make_scene(6, 20011, sigma=0.5, p_missing_view=0.2, seed=5)     # not a multiple of the tile or chunk size
+    x0 = sc.x0()
+    prob = mcc.BAProblem(sc.uvs, sc.objpoints)
+    S0, b0, g0, cost0 = prob.build_reduced(x0, lam=1e-3)
+    C = 6
+    keep = [torch.from_numpy(np.ascontiguousarray(sc.uvs)).pin_memory(),
+            torch.from_numpy(np.ascontiguousarray(sc.objpoints, dtype=np.float64)).pin_memory(),
+            torch.from_numpy(x0.copy()).pin_memory(), torch.empty(144 * C * C, dtype=torch.float64).pin_memory(),
+            torch.empty(12 * C, dtype=torch.float64).pin_memory(), torch.empty(1, dtype=torch.float64).pin_memory()]
+    ptrs = [ctypes.c_void_p(t.data_ptr()) for t in keep]
+
+    def call():
+        _native.check(lib.mcba_build_reduced_host(prob._h, ptrs[0], ptrs[1], ptrs[2], 1e-3, _native.LOSSES["soft_l1"], 1.0,
+                                                  ptrs[3], ptrs[4], ptrs[5]))
+        return keep[3].numpy().reshape(12 * C, 12 * C).copy(), keep[4].numpy().copy(), float(keep[5][0])
+
+    n0 = prob.kernel_launches
+    Sp, bp, cp = call()                                   # pipelined
+    n_pipe = prob.kernel_launches - n0
+    monkeypatch.setenv("MCBA_NO_HOST_PIPELINE", "1")
+    Sq, bq, cq = call()                                   # plain
+    monkeypatch.delenv("MCBA_NO_HOST_PIPELINE")
+    for S, b, c in ((Sp, bp, cp), (Sq, bq, cq)):
+        assert np.abs(S - S0).max() < 1e-11 * np.abs(S0).max()
+        assert np.abs(b - b0).max() < 1e-10 * np.abs(b0).max()
+        assert c == pytest.approx(cost0, rel=1e-12)
+    assert n_pipe <= 20                                   # the chunks ran on the children, not on this handle
+    # twice in a row (the children's buffers are reused), then the handle itself is still a full problem
+    Sp2, bp2, cp2 = call()
+    assert np.array_equal(Sp2, Sp) and np.array_equal(bp2, bp) and cp2 == cp
+    fresh = mcc.BAProblem(sc.uvs, sc.objpoints)
+    fresh.build_reduced(x0, lam=1e-3)
+    assert np.allclose(prob.solve_step(1e-3), fresh.solve_step(1e-3), rtol=0, atol=1e-9)   # the damped step of the system just built
+    assert np.allclose(prob.gradient(), fresh.gradient(), rtol=1e-10, atol=1e-9)
+    x, res = prob.solve(x0, verbose=0)
+    x_ref, res_ref = fresh.solve(x0, verbose=0)
+    assert res.cost == pytest.approx(res_ref.cost, rel=1e-12) and res.nfev == res_ref.nfev
