@@ -26,12 +26,15 @@ struct K2CParams {
   const double* H;       // [tile][c][63][32]
   const int* perm;       // tile slot -> frame index in x (-1 = padding)
   const unsigned int* active;   // [tile] bit c: camera c has observations in the tile
+  const int* units;      // [C][nTiles] live tiles per camera, compacted (build_units_kernel)
+  const int* unit_count; // [C]
   const double* x;       // 12C + 6F
   const CamConst* cams;
   double lambda;
   double* Z;             // [tile][row 12C][k 6][lane 32]
   double* Linv;          // [tile][21][32]
   double* y;             // [tile][6][32]
+  double* JlTau;         // [tile][12][32] J_l(rho_f) | tau_f (streamed path only: pose kernel -> rows kernel)
   double* partZy;        // [tile][12C]  sum over the tile's frames of Z_f y_f
   double* gpose;         // [f][6]
   double* D2pose;        // [tile][6][32] running max of diag(V_f)
@@ -93,11 +96,12 @@ __device__ __forceinline__ void pose_block_add(const double* __restrict__ h, con
 
 // Z_cf = (A[:,ext] E' P') L^-T for one camera, one raw camera row at a time, written as coalesced
 // rows of the tile's Z block (z points at [row 12c][k 0][lane]); zy[row] += sum_k Z[row][k] y[k].
-__device__ __forceinline__ void z_rows(const double* __restrict__ h, const double (&Rc)[9], const double (&K)[9],
-                                       const double (&Jl)[9], const double (&Linv)[21], const double (&yv)[6],
-                                       double* __restrict__ z, double (&zy)[12]) {
+template <int kRow0, int kRow1>
+__device__ __forceinline__ void z_rows_range(const double* __restrict__ h, const double (&Rc)[9], const double (&K)[9],
+                                             const double (&Jl)[9], const double (&Linv)[21], const double (&yv)[6],
+                                             double* __restrict__ z, double (&zy)[12]) {
 #pragma unroll
-  for (int row = 0; row < 12; ++row) {
+  for (int row = kRow0; row < kRow1; ++row) {
     double am[3], ag[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -119,6 +123,11 @@ __device__ __forceinline__ void z_rows(const double* __restrict__ h, const doubl
     }
     zy[row] = t;
   }
+}
+__device__ __forceinline__ void z_rows(const double* __restrict__ h, const double (&Rc)[9], const double (&K)[9],
+                                       const double (&Jl)[9], const double (&Linv)[21], const double (&yv)[6],
+                                       double* __restrict__ z, double (&zy)[12]) {
+  z_rows_range<0, 12>(h, Rc, K, Jl, Linv, yv, z, zy);
 }
 
 // lane l < 12 receives the sum over the warp of zy[l]
@@ -356,12 +365,293 @@ __global__ void __launch_bounds__(kC * 32, 2) k2c_ring_kernel(const K2CParams p)
   }
 }
 
+// Streamed path (any camera count): two kernels of unsynchronised warps, no CTA barrier and no exchange between
+// warps in the tile loops.  Every warp pulls what it needs of a pair's hand-off through its OWN two-stage ring of
+// bulk async copies (per-warp mbarriers; 18 KB per warp, kW = 12 warps per SM for up to 6 cameras):
+//   k2c_pose_kernel   one warp per FRAME TILE: rows 36..62 (A_ee, q_ext) of every live camera ->
+//                     V'' += E'^T A_ee E', g'' += E'^T q_e in registers, then the 6x6 factor of V_f + lambda D_f^2
+//                     ONCE per frame (the staged path repeats it in every camera's warp); writes L^-1, y, g_pose;
+//   k2c_rows_kernel   one warp per LIVE (tile, camera) UNIT (K2p's unit lists): rows 0..35 (A[int, ext]) -> the six
+//                     intrinsic rows of Z_cf, rows 36..56 (A_ee again: an L2 hit) -> its six extrinsic rows; Z y.
+// The staged kernel spends 14 us on a tile (six warps in step, three CTA barriers, the tile's 97 KB in one copy);
+// here a tile's pose block is ~15 us of ONE warp and its rows are spread over as many warps as it has cameras, so
+// 50,000 frames (1563 tiles, 7500 units) fill 148 x 12 warps in one round each.  Partial outputs per CTA.
+constexpr int kStreamRows = 36;                                  // rows of 32 doubles per stage
+constexpr int kStreamStage = kStreamRows * kTile;                // doubles per stage
+inline size_t k2c_stream_smem(int C, int warps) {
+  return sizeof(double) * ((size_t)warps * 2 * kStreamStage + (size_t)warps * 12 * C + (size_t)C * 12 + warps) +
+         sizeof(unsigned long long) * 2 * warps + sizeof(int) * (size_t)(C + 2);
+}
+
+struct K2cStreamShared {
+  double* ring;                 // this warp's two stages
+  double* zy_all;               // [kW][12C]
+  double* cam;                  // [C][12]: R | t
+  double* gmax;                 // [kW]
+  unsigned long long* bar;      // this warp's two mbarriers
+  int* ucum;                    // [C + 1] live units before camera c
+};
+template <int kW>
+__device__ __forceinline__ K2cStreamShared k2c_stream_carve(unsigned char* smem_raw, int C, int warp) {
+  K2cStreamShared s;
+  double* base = reinterpret_cast<double*>(smem_raw);
+  s.ring = base + (size_t)warp * 2 * kStreamStage;
+  s.zy_all = base + (size_t)kW * 2 * kStreamStage;
+  s.cam = s.zy_all + (size_t)kW * 12 * C;
+  s.gmax = s.cam + (size_t)C * 12;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(s.gmax + kW);
+  s.bar = bars + 2 * warp;
+  s.ucum = reinterpret_cast<int*>(bars + 2 * kW);
+  return s;
+}
+template <int kW>
+__device__ __forceinline__ void k2c_stream_init(const K2CParams& p, const K2cStreamShared& s, int lane) {
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(s.bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k2c_smem_u32(s.bar + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.C * 12; i += kW * 32) {
+    const CamConst& cam = p.cams[i / 12];
+    const int j = i % 12;
+    s.cam[i] = j < 9 ? cam.R[j] : cam.t[j - 9];
+  }
+}
+__device__ __forceinline__ void k2c_stream_copy(const K2cStreamShared& s, unsigned k, const double* src, unsigned rows) {
+  const unsigned b = k2c_smem_u32(s.bar + (k & 1u)), bytes = rows * kTile * (unsigned)sizeof(double);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   k2c_smem_u32(s.ring + (size_t)(k & 1u) * kStreamStage)),
+               "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+// E' of camera c for this lane's pose from the shared copy of R_c | t_c
+__device__ __forceinline__ void k2c_stream_map(const double* s_cam, int c, const double (&pose)[6], double (&Rc)[9],
+                                               double (&K)[9]) {
+  double tcf[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Rc[i] = s_cam[c * 12 + i];
+  mat3_vec(Rc, pose + 3, tcf);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) tcf[i] += s_cam[c * 12 + 9 + i];
+  cross_mat3(tcf, Rc, K);
+}
+
+template <int kW>
+__global__ void __launch_bounds__(kW * 32, 1) k2c_pose_kernel(const K2CParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = p.C, nc = 12 * C;
+  const K2cStreamShared s = k2c_stream_carve<kW>(smem_raw, C, warp);
+  k2c_stream_init<kW>(p, s, lane);
+  __syncthreads();
+  const long long gw = (long long)blockIdx.x * kW + warp, nW = (long long)gridDim.x * kW;
+  const int n_it = p.nTiles > gw ? (int)((p.nTiles - gw + nW - 1) / nW) : 0;
+  const unsigned cmask = C >= 32 ? 0xffffffffu : (1u << C) - 1u;
+  // issue side: rows 36..62 of the live cameras of this warp's tiles, two copies ahead of the consumer
+  int it_i = 0;
+  unsigned rem_i = 0, k_i = 0;
+  bool done_i = n_it == 0;
+  if (!done_i) rem_i = p.active[gw] & cmask;
+  auto issue_next = [&]() {
+    if (done_i) return;
+    while (rem_i == 0) {
+      ++it_i;
+      if (it_i >= n_it) { done_i = true; return; }
+      rem_i = p.active[gw + (long long)it_i * nW] & cmask;
+    }
+    const int c = __ffs(rem_i) - 1;
+    rem_i &= rem_i - 1;
+    if (lane == 0)
+      k2c_stream_copy(s, k_i, p.H + ((size_t)((gw + (long long)it_i * nW) * C + c) * kHandoff + 36) * kTile, 27u);
+    ++k_i;
+  };
+  unsigned k_c = 0;
+  issue_next();
+  issue_next();
+  double gmax = 0.0;
+  for (int it = 0; it < n_it; ++it) {
+    const long long tile = gw + (long long)it * nW;
+    const long long f = p.perm[tile * kTile + lane];
+    const bool fvalid = f >= 0;
+    const unsigned act = p.active[tile] & cmask;
+    double pose[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
+    double Jl[9];
+    so3_left_jacobian(pose, Jl);
+    double Vpp[21], gpp[6];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Vpp[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gpp[i] = 0.0;
+    for (unsigned m = act; m; m &= m - 1) {
+      const int c = __ffs(m) - 1;
+      double Rc[9], K[9];
+      k2c_stream_map(s.cam, c, pose, Rc, K);
+      k2c_mbar_wait(s.bar + (k_c & 1u), (k_c >> 1) & 1u);
+      pose_block_add(s.ring + (size_t)(k_c & 1u) * kStreamStage + lane - 36 * kTile, Rc, K, Vpp, gpp);   // stage row 0 = hand-off row 36
+      __syncwarp();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      ++k_c;
+      issue_next();
+    }
+    double Linv[21], yv[6], gp[6];
+    pose_block_factor(Vpp, gpp, Jl, p.lambda, p.D2pose + (size_t)tile * 6 * 32 + lane, true, Linv, yv, gp, gmax);
+    store_pose_outputs(p, tile, f, fvalid, lane, Linv, yv, gp);
+    {   // what the rows kernel needs of the pose, as coalesced rows: J_l(rho_f) and tau_f
+      double* jt = p.JlTau + (size_t)tile * 12 * kTile + lane;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) jt[i * kTile] = Jl[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) jt[(9 + i) * kTile] = pose[3 + i];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+  if (lane == 0) s.gmax[warp] = gmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double g = 0.0;
+    for (int w = 0; w < kW; ++w) g = fmax(g, s.gmax[w]);
+    p.partG[blockIdx.x] = g;
+  }
+}
+
+template <int kW>
+__global__ void __launch_bounds__(kW * 32, 1) k2c_rows_kernel(const K2CParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = p.C, nc = 12 * C;
+  const K2cStreamShared s = k2c_stream_carve<kW>(smem_raw, C, warp);
+  k2c_stream_init<kW>(p, s, lane);
+  double* s_zy = s.zy_all + (size_t)warp * nc;
+  for (int i = lane; i < nc; i += 32) s_zy[i] = 0.0;
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int c = 0; c < C; ++c) { s.ucum[c] = a; a += p.unit_count[c]; }
+    s.ucum[C] = a;
+  }
+  __syncthreads();
+  const int n_units = s.ucum[C];
+  const long long gw = (long long)blockIdx.x * kW + warp, nW = (long long)gridDim.x * kW;
+  const int n_it = n_units > gw ? (int)((n_units - gw + nW - 1) / nW) : 0;
+  // unit j of the camera-major list -> (camera, tile); j only grows, so the camera cursor only moves forward
+  auto unit_of = [&](long long j, int& c) -> long long {
+    while (j >= s.ucum[c + 1]) ++c;
+    return p.units[(long long)c * p.nTiles + (j - s.ucum[c])];
+  };
+  // Issue side, three stages per unit, two ahead of the consumer; nothing the consumer needs comes from a
+  // dependent global load (the pose kernel left L^-1, y, J_l and tau per tile as coalesced rows):
+  //   0: L^-1 (21 rows) | y (6)        1: A_ee (21 rows: hand-off rows 36..56) | J_l, tau (12)        2: A[int, ext] (36)
+  int it_i = 0, sub_i = 0, c_i = 0;
+  long long tile_i = 0;
+  unsigned k_i = 0;
+  auto issue_next = [&]() {
+    if (it_i >= n_it) return;
+    if (sub_i == 0) tile_i = unit_of(gw + (long long)it_i * nW, c_i);
+    if (lane == 0) {
+      const unsigned b = k2c_smem_u32(s.bar + (k_i & 1u));
+      double* st = s.ring + (size_t)(k_i & 1u) * kStreamStage;
+      const double* hp = p.H + (size_t)(tile_i * C + c_i) * kHandoff * kTile;
+      auto copy = [&](double* dst, const double* src, unsigned rows) {
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         k2c_smem_u32(dst)),
+                     "l"(src), "r"(rows * kTile * (unsigned)sizeof(double)), "r"(b)
+                     : "memory");
+      };
+      const unsigned rows = sub_i == 0 ? 27u : (sub_i == 1 ? 33u : 36u);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(rows * kTile * (unsigned)sizeof(double)) : "memory");
+      if (sub_i == 0) {
+        copy(st, p.Linv + (size_t)tile_i * 21 * kTile, 21u);
+        copy(st + 21 * kTile, p.y + (size_t)tile_i * 6 * kTile, 6u);
+      } else if (sub_i == 1) {
+        copy(st, hp + 36 * kTile, 21u);
+        copy(st + 21 * kTile, p.JlTau + (size_t)tile_i * 12 * kTile, 12u);
+      } else {
+        copy(st, hp, 36u);
+      }
+    }
+    ++k_i;
+    if (++sub_i == 3) { sub_i = 0; ++it_i; }
+  };
+  unsigned k_c = 0;
+  auto acquire = [&]() -> const double* {
+    k2c_mbar_wait(s.bar + (k_c & 1u), (k_c >> 1) & 1u);
+    return s.ring + (size_t)(k_c & 1u) * kStreamStage + lane;
+  };
+  auto release = [&]() {
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    ++k_c;
+    issue_next();
+  };
+  issue_next();
+  issue_next();
+  int c = 0;
+  for (int it = 0; it < n_it; ++it) {
+    const long long tile = unit_of(gw + (long long)it * nW, c);
+    double Linv[21], yv[6];
+    {
+      const double* st = acquire();
+#pragma unroll
+      for (int i = 0; i < 21; ++i) Linv[i] = st[i * kTile];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) yv[i] = st[(21 + i) * kTile];
+      release();
+    }
+    double zy[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) zy[i] = 0.0;
+    double* z = p.Z + ((size_t)(tile * nc + c * 12) * 6) * kTile + lane;
+    double Jl[9], Rc[9], K[9];
+    {
+      const double* st = acquire();
+      double pose[6] = {0.0, 0.0, 0.0, st[30 * kTile], st[31 * kTile], st[32 * kTile]};
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Jl[i] = st[(21 + i) * kTile];
+      k2c_stream_map(s.cam, c, pose, Rc, K);
+      z_rows_range<6, 12>(st - 36 * kTile, Rc, K, Jl, Linv, yv, z, zy);   // stage row 0 = hand-off row 36
+      release();
+    }
+    {
+      const double* st = acquire();
+      z_rows_range<0, 6>(st, Rc, K, Jl, Linv, yv, z, zy);
+      release();
+    }
+    const double v = zy_lane_sum(zy, lane);
+    if (lane < 12) s_zy[c * 12 + lane] += v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc; i += kW * 32) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kW; ++w) t += s.zy_all[(size_t)w * nc + i];
+    p.partZy[(size_t)blockIdx.x * nc + i] = t;
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 // K2c variant and the number of per-CTA partial outputs (Z y, max |g|) it produces.
-int k2_consumer_parts(const Layout& L, int n_sm, bool* ring) {
-  static const bool no_ring = getenv("MCBA_K2C_GENERAL") != nullptr;   // debugging: force the general path
-  *ring = !no_ring && L.C >= 2 && L.C <= 6;
-  return *ring ? (int)(L.nTiles < 2 * n_sm ? L.nTiles : 2 * n_sm) : (int)L.nTiles;
+// K2c variant (0 general, 1 staged ring, 2 streamed) and the number of per-CTA partial outputs (Z y, max |g|)
+// it produces.  MCBA_K2C_MODE = general | ring | stream overrides the choice (A/B runs, debugging).
+int k2c_stream_warps(int C) {
+  int w = 12;
+  while (w > 1 && k2c_stream_smem(C, w) > 227u * 1024u) --w;
+  return w >= 12 ? 12 : (w >= 10 ? 10 : (w >= 8 ? 8 : 4));
+}
+int k2_consumer_parts(const Layout& L, int n_sm, int* mode) {
+  static const char* forced = getenv("MCBA_K2C_MODE");
+  static const bool no_ring = getenv("MCBA_K2C_GENERAL") != nullptr;   // older switch: force the general path
+  // measured on B200: the staged ring wins where it applies (6 x 50,000: 0.076 ms against 0.023 + 0.050 ms for the
+  // streamed pair, and clearly on small shards, where one tile per warp leaves most warps of the pose kernel idle);
+  // the streamed pair replaces the general path for more cameras (16 x 25,000: 0.146 -> 0.114 ms)
+  int m = L.C >= 2 && L.C <= 6 ? 1 : 2;
+  if (no_ring) m = 0;
+  if (forced) m = forced[0] == 's' ? 2 : (forced[0] == 'r' && L.C >= 2 && L.C <= 6 ? 1 : 0);
+  *mode = m;
+  if (m == 2) return (int)(L.nTiles < n_sm ? L.nTiles : n_sm);
+  return m == 1 ? (int)(L.nTiles < 2 * n_sm ? L.nTiles : 2 * n_sm) : (int)L.nTiles;
 }
 
 int k2_producer_grid(const Layout& L, int n_sm, int* warps) {
@@ -429,17 +719,38 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
   p.H = h->d_H;
   p.perm = h->d_perm;
   p.active = h->d_active;
+  p.units = h->d_units;
+  p.unit_count = h->d_unit_count;
   p.x = x;
   p.cams = h->d_cams;
   p.lambda = lambda;
   p.Z = h->d_Z;
   p.Linv = h->d_Linv;
   p.y = h->d_y;
+  p.JlTau = h->d_JlTau;
   p.gpose = h->d_gpose;
   p.D2pose = h->d_D2pose;
   p.partG = h->d_partG;
   p.partZy = h->d_partZy;
-  if (h->k2c_ring) {
+  if (h->k2c_mode == 2) {
+    const int w = k2c_stream_warps(L.C);
+    const size_t smem = k2c_stream_smem(L.C, w);
+#define MCBA_K2C_STREAM(WV)                                                                                          \
+  do {                                                                                                               \
+    MCBA_CUDA(cudaFuncSetAttribute(k2c_pose_kernel<WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    MCBA_CUDA(cudaFuncSetAttribute(k2c_rows_kernel<WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    k2c_pose_kernel<WV><<<h->n_part_c, WV * 32, smem, h->stream>>>(p);                                               \
+    k2c_rows_kernel<WV><<<h->n_part_c, WV * 32, smem, h->stream>>>(p);                                               \
+    h->launches++;                                                                                                   \
+  } while (0)
+    switch (w) {
+      case 12: MCBA_K2C_STREAM(12); break;
+      case 10: MCBA_K2C_STREAM(10); break;
+      case 8: MCBA_K2C_STREAM(8); break;
+      default: MCBA_K2C_STREAM(4); break;
+    }
+#undef MCBA_K2C_STREAM
+  } else if (h->k2c_mode == 1) {
     const int C = L.C;
     const size_t smem = sizeof(double) * ((size_t)C * kHandoff * kTile + (size_t)C * kXchg * kTile);
     const int grid = h->n_part_c;

@@ -310,7 +310,7 @@ static int create_impl(mcba_handle* h, int C, int64_t F, int N, int device) {
   h->n_sm = prop.multiProcessorCount;
   MCBA_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->grid_frames = k2_producer_grid(L, h->n_sm, &h->prod_warps);
-  h->n_part_c = k2_consumer_parts(L, h->n_sm, &h->k2c_ring);
+  h->n_part_c = k2_consumer_parts(L, h->n_sm, &h->k2c_mode);
   h->grid_syrk = syrk_grid(L.nc, F, h->n_sm);
   h->grid_cost = (int)std::min<long long>((L.nTiles * C + 7) / 8, 8LL * h->n_sm);
   h->grid_back = (int)std::min<long long>((L.nTiles + 3) / 4, (long long)h->n_sm);   // backsub: persistent CTAs of 4 warps, whole tiles per warp
@@ -332,6 +332,7 @@ static int create_impl(mcba_handle* h, int C, int64_t F, int N, int device) {
   MCBA_ALLOC(h->d_Z, (size_t)L.Fpad * 6 * L.nc);
   MCBA_ALLOC(h->d_Linv, (size_t)L.nTiles * 21 * kTile);
   MCBA_ALLOC(h->d_y, (size_t)L.nTiles * 6 * kTile);
+  MCBA_ALLOC(h->d_JlTau, (size_t)L.nTiles * 12 * kTile);
   MCBA_ALLOC(h->d_gpose, (size_t)L.Fpad * 6);
   MCBA_ALLOC(h->d_D2pose, (size_t)L.nTiles * 6 * kTile);
   MCBA_ALLOC(h->d_D2cam, L.nc);
@@ -399,7 +400,7 @@ int mcba_destroy(mcba_handle* h) {
   for (int s = 0; s < kMaxRanks; ++s) if (h->peer_mapped[s]) cudaIpcCloseMemHandle(h->peer_mapped[s]);
   if (h->peer_block) cudaFree(h->peer_block);
   void* ptrs[] = {h->d_obs_ref, h->d_obs_tiled, h->d_obj, h->d_row_off, h->d_x, h->d_xtrial, h->d_cams, h->d_Z,
-                  h->d_Linv, h->d_y, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
+                  h->d_Linv, h->d_y, h->d_JlTau, h->d_gpose, h->d_D2pose, h->d_D2cam, h->d_partU, h->d_partS, h->d_partSyrk,
                   h->d_red, h->d_Sd, h->d_dcam, h->d_scal, h->d_info, h->d_work, h->d_Sraw, h->d_H, h->d_H_alt, h->d_partU_alt, h->d_partS_alt, h->d_cams_alt, h->d_partG, h->d_partZy, h->d_perm, h->d_mask, h->d_active, h->d_sort_tmp, h->d_units, h->d_unit_count, h->d_rowT, h->d_chunk_rows, h->d_fin_scratch, h->d_fin_counter};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->prof_ev) {

@@ -81,6 +81,7 @@ struct mcba_handle {
   double* d_Z = nullptr;
   double* d_Linv = nullptr;
   double* d_y = nullptr;
+  double* d_JlTau = nullptr;  // [nTiles][12][32] J_l(rho_f) | tau_f (streamed K2c)
   double* d_gpose = nullptr;
   double* d_D2pose = nullptr;
   double* d_D2cam = nullptr;  // running max of diag(U) (true basis), 12C
@@ -103,7 +104,7 @@ struct mcba_handle {
   unsigned long long signal_seq = 0;
   cudaEvent_t readback_done = nullptr;
   int n_part_c = 0;           // K2c partial outputs (one per tile, or one per persistent CTA on the ring path)
-  bool k2c_ring = false;
+  int k2c_mode = 0;           // 0 general, 1 staged ring (2..6 cameras), 2 streamed (k2_frames.cu)
   int grid_frames = 0, prod_warps = 8, grid_syrk = 0, grid_cost = 0, grid_back = 0;
   // solver
   cusolverDnHandle_t solver = nullptr;
@@ -172,7 +173,7 @@ int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, doubl
 int launch_k2_producer(mcba_handle* h, const double* x, int loss, double f_scale);
 int launch_k2_consumer(mcba_handle* h, const double* x, double lambda);
 int k2_producer_grid(const mcba::Layout& L, int n_sm, int* warps);
-int k2_consumer_parts(const mcba::Layout& L, int n_sm, bool* ring);
+int k2_consumer_parts(const mcba::Layout& L, int n_sm, int* mode);
 int launch_k2_syrk(mcba_handle* h);
 int syrk_grid(int nc, long long F, int n_sm);
 int launch_finalize(mcba_handle* h, bool exchange);   // exchange: sum over ranks inside the kernel (peer memory)
