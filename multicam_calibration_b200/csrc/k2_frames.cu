@@ -55,13 +55,22 @@ __device__ __forceinline__ void pose_map(const CamConst& cam, const double (&pos
 
 // Camera c's contribution to the pose block of this lane's frame: V'' += E'^T A_ee E', g'' += E'^T q_e.
 // h: this lane's hand-off column of the pair (global or shared memory), entries kTile doubles apart.
-__device__ __forceinline__ void pose_block_add(const double* __restrict__ h, const double (&Rc)[9], const double (&K)[9],
-                                               double (&Vpp)[21], double (&gpp)[6]) {
-  double Aee[21], qe[6];
+__device__ __forceinline__ void pose_block_load(const double* __restrict__ h, double (&Aee)[21], double (&qe)[6]) {
 #pragma unroll
   for (int i = 0; i < 21; ++i) Aee[i] = h[(36 + i) * kTile];
 #pragma unroll
   for (int i = 0; i < 6; ++i) qe[i] = h[(57 + i) * kTile];
+}
+__device__ __forceinline__ void pose_block_apply(const double (&Aee)[21], const double (&qe)[6], const double (&Rc)[9],
+                                                 const double (&K)[9], double (&Vpp)[21], double (&gpp)[6]);
+__device__ __forceinline__ void pose_block_add(const double* __restrict__ h, const double (&Rc)[9], const double (&K)[9],
+                                               double (&Vpp)[21], double (&gpp)[6]) {
+  double Aee[21], qe[6];
+  pose_block_load(h, Aee, qe);
+  pose_block_apply(Aee, qe, Rc, K, Vpp, gpp);
+}
+__device__ __forceinline__ void pose_block_apply(const double (&Aee)[21], const double (&qe)[6], const double (&Rc)[9],
+                                                 const double (&K)[9], double (&Vpp)[21], double (&gpp)[6]) {
   double Be[36];
 #pragma unroll
   for (int r = 0; r < 6; ++r) {
@@ -494,7 +503,7 @@ __global__ void __launch_bounds__(kW * 32, 1) k2c_pose_kernel(const K2CParams p)
       __syncwarp();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       ++k_c;
-      issue_next();
+      issue_next();   // (refilling the stage before the arithmetic, from a register copy, was slower: 23 -> 28 us)
     }
     double Linv[21], yv[6], gp[6];
     pose_block_factor(Vpp, gpp, Jl, p.lambda, p.D2pose + (size_t)tile * 6 * 32 + lane, true, Linv, yv, gp, gmax);
@@ -634,7 +643,8 @@ __global__ void __launch_bounds__(kW * 32, 1) k2c_rows_kernel(const K2CParams p)
 // ------------------------------------------------------------------ launchers
 // K2c variant and the number of per-CTA partial outputs (Z y, max |g|) it produces.
 // K2c variant (0 general, 1 staged ring, 2 streamed) and the number of per-CTA partial outputs (Z y, max |g|)
-// it produces.  MCBA_K2C_MODE = general | ring | stream overrides the choice (A/B runs, debugging).
+// it produces: 0 general, 1 staged ring, 2 streamed pair.
+// MCBA_K2C_MODE = general | ring | stream overrides the choice (A/B runs, debugging).
 int k2c_stream_warps(int C) {
   int w = 12;
   while (w > 1 && k2c_stream_smem(C, w) > 227u * 1024u) --w;

@@ -104,7 +104,7 @@ struct mcba_handle {
   unsigned long long signal_seq = 0;
   cudaEvent_t readback_done = nullptr;
   int n_part_c = 0;           // K2c partial outputs (one per tile, or one per persistent CTA on the ring path)
-  int k2c_mode = 0;           // 0 general, 1 staged ring (2..6 cameras), 2 streamed (k2_frames.cu)
+  int k2c_mode = 0;           // 0 general, 1 staged ring (2..6 cameras), 2 streamed pair (k2_frames.cu)
   int grid_frames = 0, prod_warps = 8, grid_syrk = 0, grid_cost = 0, grid_back = 0;
   // solver
   cusolverDnHandle_t solver = nullptr;
