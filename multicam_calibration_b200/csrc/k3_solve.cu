@@ -71,8 +71,11 @@ struct SolveParams {
 };
 
 // kT: trailing tiles per warp (3: up to 6 cameras, 8: up to 10, 19: up to 16 -- 24 * 25 / 2 = 300 tiles of the
-// 200-row augmented system over 16 warps; that variant spills part of its accumulators to local memory)
-template <int kT>
+// 200-row augmented system over 16 warps).  kSmemAcc (the 19-tile variant): 38 accumulators per lane beside the
+// panel's 8 x 8 block do not fit in 128 registers (they spilled to local memory: 0.116 ms for 192 x 192), so that
+// variant keeps the tiles where they already live -- the packed matrix in shared memory -- and every update is
+// load, two DMMAs, store; the 19 tiles of a warp are independent, so their round trips overlap.
+template <int kT, bool kSmemAcc = false>
 __global__ void __launch_bounds__(kSolveThreads, 1) solve_reduced_kernel(const SolveParams p) {
   extern __shared__ double A[];                 // packed lower triangle of the augmented matrix, n1p rows
   __shared__ double s_inv[kSolveMaxN + 8];      // 1 / L_jj
@@ -139,8 +142,8 @@ __global__ void __launch_bounds__(kSolveThreads, 1) solve_reduced_kernel(const S
       const int ib = jb + rem;
       tij[s] = (ib << 8) | jb;
       const int cr = ib * 8 + fr, cc = jb * 8 + fc;
-      if (cc <= cr) acc[s][0] = A[pk(cr, cc)];
-      if (cc + 1 <= cr) acc[s][1] = A[pk(cr, cc + 1)];
+      if (!kSmemAcc && cc <= cr) acc[s][0] = A[pk(cr, cc)];
+      if (!kSmemAcc && cc + 1 <= cr) acc[s][1] = A[pk(cr, cc + 1)];
     }
   }
   MCBA_STAMP(2);
@@ -212,18 +215,28 @@ __global__ void __launch_bounds__(kSolveThreads, 1) solve_reduced_kernel(const S
     // both slower than this plain loop with a warp-uniform test per slot)
     const int kb = k0 >> 3;
     const int fk = k0 + (lane & 3);
+    // (a straight-line version of the shared-memory variant -- dead slots computing on a valid row pair and storing
+    // nothing, so that the slots' chains can overlap -- was slower: 0.146 ms against 0.094 ms at 192 x 192)
 #pragma unroll
     for (int s = 0; s < kT; ++s) {
       const int jb = tij[s] & 0xff, ib = tij[s] >> 8;
       if (tij[s] >= 0 && jb > kb) {     // warp-uniform
         const double a0 = -A[pk(ib * 8 + fr, fk)], a1 = -A[pk(ib * 8 + fr, fk + 4)];
         const double b0 = A[pk(jb * 8 + fr, fk)], b1 = A[pk(jb * 8 + fr, fk + 4)];
-        solve_dmma(acc[s][0], acc[s][1], a0, b0);
-        solve_dmma(acc[s][0], acc[s][1], a1, b1);
-        if (jb == kb + 1) {             // the next panel: back to shared memory
-          const int cr = ib * 8 + fr, cc = jb * 8 + fc;
-          if (cc <= cr) A[pk(cr, cc)] = acc[s][0];
-          if (cc + 1 <= cr) A[pk(cr, cc + 1)] = acc[s][1];
+        const int cr = ib * 8 + fr, cc = jb * 8 + fc;
+        if (kSmemAcc) {                 // the tile lives in shared memory (fragments read the panel's columns only)
+          double c0 = cc <= cr ? A[pk(cr, cc)] : 0.0, c1 = cc + 1 <= cr ? A[pk(cr, cc + 1)] : 0.0;
+          solve_dmma(c0, c1, a0, b0);
+          solve_dmma(c0, c1, a1, b1);
+          if (cc <= cr) A[pk(cr, cc)] = c0;
+          if (cc + 1 <= cr) A[pk(cr, cc + 1)] = c1;
+        } else {
+          solve_dmma(acc[s][0], acc[s][1], a0, b0);
+          solve_dmma(acc[s][0], acc[s][1], a1, b1);
+          if (jb == kb + 1) {           // the next panel: back to shared memory
+            if (cc <= cr) A[pk(cr, cc)] = acc[s][0];
+            if (cc + 1 <= cr) A[pk(cr, cc + 1)] = acc[s][1];
+          }
         }
       }
     }
@@ -295,14 +308,16 @@ int solve_reduced(mcba_handle* h, double lambda) {
     const int n1p = (nc + 1 + 7) & ~7;
     const size_t smem = sizeof(double) * (size_t)n1p * (n1p + 1) / 2;
     const int nb = n1p / 8, per_warp = ((nb - 1) * nb / 2 + kSolveWarps - 1) / kSolveWarps;
-#define MCBA_SOLVE(T)                                                                                            \
-  do {                                                                                                           \
-    MCBA_CUDA(cudaFuncSetAttribute(solve_reduced_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    solve_reduced_kernel<T><<<1, kSolveThreads, smem, h->stream>>>(p);                                           \
+#define MCBA_SOLVE(...)                                                                                                    \
+  do {                                                                                                                     \
+    MCBA_CUDA(cudaFuncSetAttribute(solve_reduced_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    solve_reduced_kernel<__VA_ARGS__><<<1, kSolveThreads, smem, h->stream>>>(p);                                           \
   } while (0)
+    static const bool wide_in_registers = getenv("MCBA_SOLVE_WIDE_REGS") != nullptr;   // A/B: the spilling variant
     if (per_warp <= 3) MCBA_SOLVE(3);
     else if (per_warp <= 8) MCBA_SOLVE(8);
-    else MCBA_SOLVE(19);
+    else if (wide_in_registers) MCBA_SOLVE(19);
+    else MCBA_SOLVE(19, true);
 #undef MCBA_SOLVE
 #ifdef MCBA_SOLVE_TIMING
     {
