@@ -758,7 +758,7 @@ def run_engine(args):
             "kernels_ms": kernels_block(main["kernels_ms"]),
             "e2e": {"value": main["n_obs_total"] / (e["ms_pinned"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e["h2d"],
                     "d2h_bytes_per_step": e["d2h"], "ms_per_step": e["ms_pinned"], "steps": e["steps"],
-                    "call": "mcba_build_reduced_host (pinned host uvs, objpoints, x -> S, b, cost)",
+                    "call": "mcba_build_reduced_host (pinned host uvs, objpoints, x -> S, b, cost); at one rank the observations cross PCIe in 8 frame ranges, each evaluated while the next is in flight",
                     "pageable": {"value": main["n_obs_total"] / (e["ms_pageable"] * 1e-3), "ms_per_step": e["ms_pageable"],
                                  "call": "the same call on pageable numpy arrays (staged through mcba_upload's bounce buffers)"}},
             "gpu_launches": main["launches"],
