@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
   double* s_T = k1_smem + (size_t)warp * kChunkFrames * 12;          // [32 rows][12]
   double* s_cam = k1_smem + (size_t)nWarps * kChunkFrames * 12;       // [C][18]: fx fy cx cy k1 k2 | R (9) | t (3)
   double* s_obj = s_cam + (size_t)C * 18;                             // [3 N]
+  int* s_rk = reinterpret_cast<int*>(s_obj + ((3 * N + 1) & ~1)) + warp * kChunkFrames;   // [32] row of the q-th LIVE row of the chunk
   for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) s_obj[i] = obj[i];
   if (threadIdx.x < C) {   // camera constants in the kernel itself: no separate launch in front of it
     const double* p = x + 12 * threadIdx.x;
@@ -367,8 +368,15 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
     const int nf = (int)(F - f0 < kChunkFrames ? F - f0 : kChunkFrames);
     const double* sc = s_cam + 18 * c;
     const Intr in{sc[0], sc[1], sc[2], sc[3], sc[4], sc[5]};
-    __syncwarp();   // the previous chunk's readers are done with s_T
-    if (lane < nf) {
+    // Rows (camera, frame) without a single detection -- a camera that did not see the board -- are known from
+    // the counting pass.  Only the LIVE rows are walked: their transforms and row numbers are stored by rank, and
+    // the slot loop runs over rank * N + corner, so a dead row costs neither loads nor instructions.
+    const unsigned rows = kCompact ? chunk_rows[u] : (nf >= 32 ? 0xffffffffu : (1u << nf) - 1u);
+    const int n_live = __popc(rows);
+    const int rank = __popc(rows & lt);
+    __syncwarp();   // the previous chunk's readers are done with s_T and s_rk
+    if ((rows >> lane) & 1u) {
+      s_rk[rank] = lane;
       const double* ps = x + 12 * (long long)C + 6 * (f0 + lane);
       const double rho[3] = {ps[0], ps[1], ps[2]}, tau[3] = {ps[3], ps[4], ps[5]};
       double Rc[9], Rp[9], Rcf[9], tcf[3];
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
       rodrigues(rho, Rp);
       mat3_mul(Rc, Rp, Rcf);
       mat3_vec(Rc, tau, tcf);
-      double2* t = reinterpret_cast<double2*>(s_T + lane * 12);
+      double2* t = reinterpret_cast<double2*>(s_T + rank * 12);
       t[0] = make_double2(Rcf[0], Rcf[1]);
       t[1] = make_double2(Rcf[2], Rcf[3]);
       t[2] = make_double2(Rcf[4], Rcf[5]);
@@ -386,14 +394,11 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
       t[5] = make_double2(tcf[1] + sc[16], tcf[2] + sc[17]);
     }
     __syncwarp();
-    const int total = nf * N;
+    const int total = n_live * N;                           // slots of the live rows, in the reference order
     const long long base = ((long long)c * F + f0) * N;     // first slot of the chunk
     // the chunk's residuals start at its scanned offset; positions inside the chunk are 32-bit
     double* out_c = out + (kCompact ? chunk_off[u] : 0);
     int off = 0;
-    // rows (camera, frame) without a single detection -- a camera that did not see the board -- are
-    // known from the counting pass: their 16 N bytes of NaN are not read again
-    const unsigned rows = kCompact ? chunk_rows[u] : 0u;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
     constexpr int kU = 4;
     // four groups of 32 slots per step; a step that lies wholly inside the chunk runs without any
@@ -405,7 +410,10 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
       for (int g = 0; g < kU; ++g) {
         const int i = i0 + g * 32 + lane;
         o[g] = make_double2(qnan, qnan);
-        if (kCompact && (!kChecked || i < total) && ((rows >> __umulhi((unsigned)i, inv_n)) & 1u)) o[g] = ref[base + i];
+        if (kCompact && (!kChecked || i < total)) {
+          const int q = (int)__umulhi((unsigned)i, inv_n);
+          o[g] = ref[base + (s_rk[q] - q) * N + i];
+        }
       }
 #pragma unroll
       for (int g = 0; g < kU; ++g) {
@@ -414,9 +422,9 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
         bool fu = false, fv = false;
         double ru = 0.0, rv = 0.0;
         if (!kChecked || i < total) {
-          const int row = (int)__umulhi((unsigned)i, inv_n);
-          const int n = i - row * N;
-          const double2* t = reinterpret_cast<const double2*>(s_T + row * 12);
+          const int q = (int)__umulhi((unsigned)i, inv_n);   // rank of the slot's row among the live rows
+          const int n = i - q * N;
+          const double2* t = reinterpret_cast<const double2*>(s_T + q * 12);
           const double2 t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3], t4 = t[4], t5 = t[5];
           const double Rcf[9] = {t0.x, t0.y, t1.x, t1.y, t2.x, t2.y, t3.x, t3.y, t4.x};
           const double tcf[3] = {t4.y, t5.x, t5.y};
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(256, MCBA_K1_CTAS) residual_chunks_kernel(cons
             ru = o[g].x - pu;
             rv = o[g].y - pv;
           } else {
-            reinterpret_cast<double2*>(out)[base + i] = make_double2(pu, pv);
+            reinterpret_cast<double2*>(out)[base + i] = make_double2(pu, pv);   // all rows live here: rank = row
           }
         }
         if (kCompact) {
@@ -457,7 +465,8 @@ static int launch_chunks(mcba_handle* h, const double* x, double* out, bool comp
   const int warps = 8;
   const long long nBlk = (L.F + kChunkFrames - 1) / kChunkFrames;
   const long long units = (long long)L.C * nBlk;
-  const size_t smem = sizeof(double) * ((size_t)warps * kChunkFrames * 12 + 18 * (size_t)L.C + 3 * (size_t)L.N);
+  const size_t smem = sizeof(double) * ((size_t)warps * kChunkFrames * 12 + 18 * (size_t)L.C + ((3 * (size_t)L.N + 1) & ~(size_t)1)) +
+                      sizeof(int) * (size_t)warps * kChunkFrames;
   long long grid = (units + warps - 1) / warps;
   if (grid > 8LL * h->n_sm) grid = 8LL * h->n_sm;
   if (smem > 48 * 1024) {
