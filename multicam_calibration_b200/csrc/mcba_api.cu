@@ -550,13 +550,14 @@ struct HostPipe {
   cudaEvent_t begin = nullptr;
   const double** d_table = nullptr;   // the children's packed systems (device pointers, fixed)
   // One CUDA graph per range: its ~25 operations (three slice copies, masks, sort, tiling, unit lists, memsets, the
-  // four kernels of the evaluation) are captured on the second call and replayed with ONE launch afterwards -- the
+  // four kernels of the evaluation) are captured on the second call with the same lambda / loss / f_scale and replayed with ONE launch afterwards -- the
   // host otherwise spends ~180 driver calls per call of the pipeline, which on a slow or busy host delays the
   // ranges' work behind their transfers (3.4 -> 3.8-3.9 ms observed).  Re-captured when lambda / loss / f_scale change.
   std::vector<cudaGraphExec_t> graphs;
   std::vector<char> warmed;           // the range ran once un-captured (first-use allocations are done)
   double g_lambda = 0.0, g_f_scale = 0.0;
   int g_loss = -1;
+  int same_params_calls = 0;          // consecutive calls with these values: a caller that varies lambda never captures
   bool parent_stale = false;          // the last call's observations are in the children only
   double lambda = 0.0, f_scale = 1.0; // ... and so is its evaluation (re-run on the parent when it is needed)
   int loss = 0;
@@ -685,6 +686,9 @@ static int build_reduced_host_pipelined(mcba_handle* h, const double* h_uvs, con
   if (lambda != P.g_lambda || loss != P.g_loss || f_scale != P.g_f_scale) {   // the graphs bake these in
     for (cudaGraphExec_t& g : P.graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     P.g_lambda = lambda; P.g_loss = loss; P.g_f_scale = f_scale;
+    P.same_params_calls = 0;
+  } else {
+    ++P.same_params_calls;
   }
   // what a range does once its observations have landed (compute stream)
   auto range_work = [&](int k) -> int {
@@ -702,7 +706,7 @@ static int build_reduced_host_pipelined(mcba_handle* h, const double* h_uvs, con
     MCBA_CUDA(cudaStreamWaitEvent(h->stream, P.landed[k], 0));
     if (P.graphs[k]) {
       MCBA_CUDA(cudaGraphLaunch(P.graphs[k], h->stream));
-    } else if (P.warmed[k] && !no_graphs) {
+    } else if (P.warmed[k] && !no_graphs && P.same_params_calls >= 1) {
       cudaGraph_t graph = nullptr;
       MCBA_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       rc = range_work(k);

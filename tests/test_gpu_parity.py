@@ -729,8 +729,8 @@ def test_host_buffer_call_pipelined_equals_plain_and_leaves_the_problem_usable(m
             torch.empty(12 * C, dtype=torch.float64).pin_memory(), torch.empty(1, dtype=torch.float64).pin_memory()]
     ptrs = [ctypes.c_void_p(t.data_ptr()) for t in keep]
 
-    def call():
-        _native.check(lib.mcba_build_reduced_host(prob._h, ptrs[0], ptrs[1], ptrs[2], 1e-3, _native.LOSSES["soft_l1"], 1.0,
+    def call(lam=1e-3):
+        _native.check(lib.mcba_build_reduced_host(prob._h, ptrs[0], ptrs[1], ptrs[2], lam, _native.LOSSES["soft_l1"], 1.0,
                                                   ptrs[3], ptrs[4], ptrs[5]))
         return keep[3].numpy().reshape(12 * C, 12 * C).copy(), keep[4].numpy().copy(), float(keep[5][0])
 
@@ -749,6 +749,16 @@ def test_host_buffer_call_pipelined_equals_plain_and_leaves_the_problem_usable(m
     Sp2, bp2, cp2 = call()
     assert np.array_equal(Sp2, Sp) and np.array_equal(bp2, bp) and cp2 == cp
     fresh = mcc.BAProblem(sc.uvs, sc.objpoints)
+    # a third call with the same arguments replays the ranges' CUDA graphs; a different damping drops them
+    Sp3, bp3, cp3 = call()
+    assert np.array_equal(Sp3, Sp) and np.array_equal(bp3, bp) and cp3 == cp
+    S1, b1, g1, cost1 = fresh.build_reduced(x0, lam=1e-1)
+    for _ in range(3):
+        Sl, bl, cl = call(1e-1)
+        assert np.abs(Sl - S1).max() < 1e-11 * np.abs(S1).max() and np.abs(bl - b1).max() < 1e-10 * np.abs(b1).max()
+    assert np.abs(S1 - S0).max() > 1e-6 * np.abs(S0).max()      # the damping did change the system
+    Sp4, bp4, cp4 = call()
+    assert np.array_equal(Sp4, Sp) and np.array_equal(bp4, bp)
     fresh.build_reduced(x0, lam=1e-3)
     assert np.allclose(prob.solve_step(1e-3), fresh.solve_step(1e-3), rtol=0, atol=1e-9)   # the damped step of the system just built
     assert np.allclose(prob.gradient(), fresh.gradient(), rtol=1e-10, atol=1e-9)
