@@ -470,8 +470,8 @@ static int launch_chunks(mcba_handle* h, const double* x, double* out, bool comp
   long long grid = (units + warps - 1) / warps;
   if (grid > 8LL * h->n_sm) grid = 8LL * h->n_sm;
   if (smem > 48 * 1024) {
-    MCBA_CUDA(cudaFuncSetAttribute(residual_chunks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MCBA_CUDA(cudaFuncSetAttribute(residual_chunks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MCBA_CUDA(set_dynamic_smem((const void*)residual_chunks_kernel<true>, smem));
+    MCBA_CUDA(set_dynamic_smem((const void*)residual_chunks_kernel<false>, smem));
   }
   if (compact)
     residual_chunks_kernel<true><<<(int)grid, warps * 32, smem, h->stream>>>(

@@ -677,7 +677,7 @@ int k2_producer_grid(const Layout& L, int n_sm, int* warps) {
 template <int kLoss, int kWarps>
 static int launch_k2p_t(mcba_handle* h, const K2PParams& p) {
   const size_t smem = k2p_smem(p.C, p.N, kWarps);
-  MCBA_CUDA(cudaFuncSetAttribute(k2p_kernel<kLoss, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MCBA_CUDA(set_dynamic_smem((const void*)k2p_kernel<kLoss, kWarps>, smem));
   k2p_kernel<kLoss, kWarps><<<h->grid_frames, kWarps * 32, smem, h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
@@ -747,8 +747,8 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
     const size_t smem = k2c_stream_smem(L.C, w);
 #define MCBA_K2C_STREAM(WV)                                                                                          \
   do {                                                                                                               \
-    MCBA_CUDA(cudaFuncSetAttribute(k2c_pose_kernel<WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    MCBA_CUDA(cudaFuncSetAttribute(k2c_rows_kernel<WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    MCBA_CUDA(set_dynamic_smem((const void*)k2c_pose_kernel<WV>, smem));    \
+    MCBA_CUDA(set_dynamic_smem((const void*)k2c_rows_kernel<WV>, smem));    \
     k2c_pose_kernel<WV><<<h->n_part_c, WV * 32, smem, h->stream>>>(p);                                               \
     k2c_rows_kernel<WV><<<h->n_part_c, WV * 32, smem, h->stream>>>(p);                                               \
     h->launches++;                                                                                                   \
@@ -766,7 +766,7 @@ int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {
     const int grid = h->n_part_c;
 #define MCBA_K2C_RING(CV)                                                                                          \
   do {                                                                                                             \
-    MCBA_CUDA(cudaFuncSetAttribute(k2c_ring_kernel<CV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    MCBA_CUDA(set_dynamic_smem((const void*)k2c_ring_kernel<CV>, smem));  \
     k2c_ring_kernel<CV><<<grid, CV * 32, smem, h->stream>>>(p);                                                     \
   } while (0)
     switch (C) {

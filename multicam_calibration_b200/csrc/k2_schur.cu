@@ -342,7 +342,7 @@ int launch_k2_syrk(mcba_handle* h) {
   static const bool no_static = getenv("MCBA_SYRK_RUNTIME") != nullptr;   // A/B: run-time tile lists
 #define MCBA_SYRK(W, NB)                                                                                          \
   do {                                                                                                            \
-    MCBA_CUDA(cudaFuncSetAttribute(k2_syrk_kernel<W, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem)); \
+    MCBA_CUDA(set_dynamic_smem((const void*)k2_syrk_kernel<W, NB>, c.smem)); \
     k2_syrk_kernel<W, NB><<<dim3(h->grid_syrk, c.gy), (W + 1) * 32, c.smem, h->stream>>>(p);                      \
   } while (0)
   const int nb = (c.gy == 1 && !no_static) ? p.nb8 : 0;
@@ -863,7 +863,7 @@ int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda
   p.counter = reinterpret_cast<unsigned int*>(h->d_scal + 33);
   p.out = h->d_scal + 8;
   const size_t smem = sizeof(double) * ((size_t)kBackWarps * kBackStages * kBackStageDoubles + (size_t)((L.nc + 1) & ~1));
-  MCBA_CUDA(cudaFuncSetAttribute(backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  MCBA_CUDA(set_dynamic_smem((const void*)backsub_kernel, smem));
   backsub_kernel<<<h->grid_back, kBackWarps * 32, smem, h->stream>>>(p);
   h->launches++;
   MCBA_CUDA(cudaGetLastError());

@@ -310,7 +310,7 @@ int solve_reduced(mcba_handle* h, double lambda) {
     const int nb = n1p / 8, per_warp = ((nb - 1) * nb / 2 + kSolveWarps - 1) / kSolveWarps;
 #define MCBA_SOLVE(...)                                                                                                    \
   do {                                                                                                                     \
-    MCBA_CUDA(cudaFuncSetAttribute(solve_reduced_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    MCBA_CUDA(set_dynamic_smem((const void*)solve_reduced_kernel<__VA_ARGS__>, smem)); \
     solve_reduced_kernel<__VA_ARGS__><<<1, kSolveThreads, smem, h->stream>>>(p);                                           \
   } while (0)
     static const bool wide_in_registers = getenv("MCBA_SOLVE_WIDE_REGS") != nullptr;   // A/B: the spilling variant

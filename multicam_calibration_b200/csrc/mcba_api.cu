@@ -9,12 +9,29 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "mcba_internal.h"
 #include "mcba_peer.cuh"
 
 namespace mcba {
+
+cudaError_t set_dynamic_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, size_t> granted;   // (kernel, device) -> bytes
+  int device = 0;
+  cudaError_t e = cudaGetDevice(&device);
+  if (e != cudaSuccess) return e;
+  const unsigned long long key = (unsigned long long)reinterpret_cast<uintptr_t>(kernel) * 64ull + (unsigned)device;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = granted.find(key);
+  if (it != granted.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) granted[key] = bytes;
+  return e;
+}
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }

@@ -37,6 +37,12 @@ struct Layout {
 
 }  // namespace mcba
 
+namespace mcba {
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device) and size instead of a driver call in front
+// of every launch (the attribute is a maximum: it only ever grows).  ~1 us each, five of them per LM iteration on the
+// host's critical path between the trial's scalars and the next evaluation.
+cudaError_t set_dynamic_smem(const void* kernel, size_t bytes);
+}
 namespace mcba { struct HostPipe; }
 
 struct mcba_handle {
