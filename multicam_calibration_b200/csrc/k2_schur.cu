@@ -687,6 +687,7 @@ struct BackParams {
   long long F, nTiles;
   const CamConst* cams;
   const int* perm;      // tile slot -> frame index in x (-1 = padding)
+  const unsigned int* active;   // [tile] bit c: camera c has observations in the tile (its Z rows are zero otherwise)
   const double* x;
   double* x_new;
   const double* dcam;   // true-basis camera step (12C)
@@ -719,21 +720,33 @@ __global__ void __launch_bounds__(kBackWarps * 32, 1) backsub_kernel(const BackP
   }
   __syncthreads();
 
-  // this warp's tiles: gw, gw + W, ...; its stream of stages: (tile, camera) in order
+  // this warp's tiles: gw, gw + W, ...; its stream of stages: the LIVE (tile, camera) units in order -- the Z rows
+  // of a camera that did not see the tile's frames are zero (never written) and are not read either
   const long long gw = (long long)blockIdx.x * kBackWarps + warp, W = (long long)gridDim.x * kBackWarps;
   const int chunks = nc / kBackRows;
+  const unsigned cmask = chunks >= 32 ? 0xffffffffu : (1u << chunks) - 1u;
   const long long my_tiles = p.nTiles > gw ? (p.nTiles - gw + W - 1) / W : 0;
-  const long long n_units = my_tiles * chunks;
-  auto issue = [&](long long q) {   // lane 0 only: stage q of this warp's stream
-    const long long tile = gw + (q / chunks) * W;
-    const int ch = (int)(q % chunks), s = (int)(q % kBackStages);
-    constexpr unsigned bytes = kBackStageDoubles * sizeof(double);
-    mbar_expect_tx(&full_bar[warp][s], bytes);
-    tma_load_1d(ring + (size_t)s * kBackStageDoubles, p.Z + ((size_t)tile * nc + (size_t)ch * kBackRows) * 6 * kTile, bytes,
-                &full_bar[warp][s]);
+  long long it_i = 0, k_i = 0;             // issue cursor (all lanes keep it; lane 0 issues)
+  unsigned rem_i = my_tiles > 0 ? (p.active[gw] & cmask) : 0u;
+  auto issue_next = [&]() {
+    while (rem_i == 0) {
+      if (++it_i >= my_tiles) { it_i = my_tiles; return; }
+      rem_i = p.active[gw + it_i * W] & cmask;
+    }
+    const int ch = __ffs(rem_i) - 1;
+    rem_i &= rem_i - 1;
+    if (lane == 0) {
+      const long long tile = gw + it_i * W;
+      const int s = (int)(k_i % kBackStages);
+      constexpr unsigned bytes = kBackStageDoubles * sizeof(double);
+      mbar_expect_tx(&full_bar[warp][s], bytes);
+      tma_load_1d(ring + (size_t)s * kBackStageDoubles, p.Z + ((size_t)tile * nc + (size_t)ch * kBackRows) * 6 * kTile, bytes,
+                  &full_bar[warp][s]);
+    }
+    ++k_i;
   };
-  if (lane == 0)
-    for (long long q = 0; q < kBackStages && q < n_units; ++q) issue(q);
+  for (int s0 = 0; s0 < kBackStages; ++s0)
+    if (it_i < my_tiles) issue_next();
 
   double dd = 0, xx = 0, gd = 0, dDd = 0;
   long long q = 0;
@@ -751,7 +764,8 @@ __global__ void __launch_bounds__(kBackWarps * 32, 1) backsub_kernel(const BackP
       for (int k = 0; k < 21; ++k) li[k] = lo[k * kTile];
     }
     double s[6] = {0, 0, 0, 0, 0, 0};
-    for (int ch = 0; ch < chunks; ++ch, ++q) {
+    for (unsigned m = p.active[tile] & cmask; m; m &= m - 1, ++q) {
+      const int ch = __ffs(m) - 1;
       const int st = (int)(q % kBackStages);
       mbar_wait(&full_bar[warp][st], (unsigned)((q / kBackStages) & 1));
       const double* z = ring + (size_t)st * kBackStageDoubles + lane;
@@ -764,7 +778,7 @@ __global__ void __launch_bounds__(kBackWarps * 32, 1) backsub_kernel(const BackP
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our reads of the stage precede the copy that refills it
       __syncwarp();
-      if (lane == 0 && q + kBackStages < n_units) issue(q + kBackStages);
+      if (it_i < my_tiles) issue_next();
     }
     if (f >= 0) {
 #pragma unroll
@@ -856,7 +870,7 @@ int launch_backsub(mcba_handle* h, const double* x, double* x_new, double lambda
   const Layout& L = h->L;
   BackParams p;
   p.C = L.C; p.nc = L.nc; p.rank = h->rank; p.F = L.F; p.nTiles = L.nTiles;
-  p.cams = h->d_cams; p.perm = h->d_perm; p.x = x; p.x_new = x_new; p.dcam = h->d_dcam;
+  p.cams = h->d_cams; p.perm = h->d_perm; p.active = h->d_active; p.x = x; p.x_new = x_new; p.dcam = h->d_dcam;
   p.Z = h->d_Z; p.Linv = h->d_Linv; p.y = h->d_y; p.gpose = h->d_gpose; p.D2pose = h->d_D2pose;
   p.D2cam = h->d_D2cam; p.gcam = h->d_red + L.offG;
   p.part = h->d_scal + 64 + 3 * 4096;                                     // [grid_back][4]
