@@ -12,6 +12,8 @@
 //       (lane = frame is the fastest index of H, Z, y, L^-1).  HBM bound: reads 504 B,
 //       writes 576 B per pair.
 //
+// K2c comes in three builds (k2_consumer_parts): the staged ring for 2-6 cameras, a streamed pair of kernels
+// (pose block per tile, Z rows per live unit) for any other count, and the plain general kernel as the fall-back.
 // A rejected LM step only changes lambda: K2c is re-run on the same hand-off, K2p is not.
 #include <cstdlib>
 

@@ -550,9 +550,11 @@ int mcba_build_reduced(mcba_handle* h, const double* d_x, double lambda, int los
 // frames the observations instead cross in kHostChunks frame ranges on a copy stream; every range is a
 // complete small problem of its own (a child handle: tiled, evaluated and reduced while the next range
 // is in flight), and S, b, the camera gradient and the scalars of the ranges, all sums over frames,
-// are added at the end (the additivity tests/test_gpu_parity.py checks for shards).  Afterwards
-// the parent's own copy of the observations is refreshed from the children asynchronously, so the
-// handle is left as after mcba_set_observations.  MCBA_NO_HOST_PIPELINE=1 forces the plain path.
+// are added at the end (the additivity tests/test_gpu_parity.py checks for shards).  The parent's own
+// tiled copy and evaluation are rebuilt from the children when a later call needs them (need_obs), so
+// the handle behaves as after mcba_set_observations + mcba_build_reduced.  A range's work is replayed
+// from one CUDA graph once the caller's lambda / loss / f_scale have been stable for two calls.
+// MCBA_NO_HOST_PIPELINE=1 forces the plain path, MCBA_NO_PIPE_GRAPHS=1 the kernel-by-kernel issue.
 namespace mcba {
 constexpr int kHostChunks = 8;
 constexpr long long kHostPipeMinFrames = 16384;
