@@ -642,6 +642,62 @@ __global__ void __launch_bounds__(kW * 32, 1) k2c_rows_kernel(const K2CParams p)
   }
 }
 
+// The evaluation that closes a solve needs neither Z nor the factor: only the pose gradient
+// g_f = P'^T sum_c E'^T q_ext (and max |g|, the optimality).  One warp per frame tile reads the six q_ext rows of
+// every live camera straight from the hand-off (coalesced 256-byte rows): 10 % of K2c's reads, none of its writes.
+__global__ void __launch_bounds__(128) k2c_grad_kernel(const K2CParams p) {
+  __shared__ double s_g[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kW = blockDim.x >> 5;
+  const int C = p.C, nc = 12 * C;
+  const unsigned cmask = C >= 32 ? 0xffffffffu : (1u << C) - 1u;
+  double gmax = 0.0;
+  for (long long tile = (long long)blockIdx.x * kW + warp; tile < p.nTiles; tile += (long long)gridDim.x * kW) {
+    const long long f = p.perm[tile * kTile + lane];
+    const bool fvalid = f >= 0;
+    double pose[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) pose[i] = fvalid ? p.x[(size_t)nc + f * 6 + i] : 0.0;
+    double Jl[9];
+    so3_left_jacobian(pose, Jl);
+    double gpp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (unsigned m = p.active[tile] & cmask; m; m &= m - 1) {
+      const int c = __ffs(m) - 1;
+      double Rc[9], K[9], qe[6];
+      pose_map(p.cams[c], pose, Rc, K);
+      const double* h = p.H + ((size_t)(tile * C + c) * kHandoff + 57) * kTile + lane;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) qe[i] = h[i * kTile];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {   // the g'' part of pose_block_apply
+        gpp[a] += Rc[a] * qe[0] + Rc[3 + a] * qe[1] + Rc[6 + a] * qe[2] + K[a] * qe[3] + K[3 + a] * qe[4] + K[6 + a] * qe[5];
+        gpp[3 + a] += Rc[a] * qe[3] + Rc[3 + a] * qe[4] + Rc[6 + a] * qe[5];
+      }
+    }
+    double gp[6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {     // g = P'^T g'' (pose_block_factor)
+      gp[i] = Jl[i] * gpp[0] + Jl[3 + i] * gpp[1] + Jl[6 + i] * gpp[2];
+      gp[3 + i] = gpp[3 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gmax = fmax(gmax, fabs(gp[i]));
+    if (fvalid) {
+#pragma unroll
+      for (int i = 0; i < 6; i += 2)
+        *reinterpret_cast<double2*>(p.gpose + (size_t)f * 6 + i) = make_double2(gp[i], gp[i + 1]);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+  if (lane == 0) s_g[warp] = gmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double g = 0.0;
+    for (int w = 0; w < kW; ++w) g = fmax(g, s_g[w]);
+    p.partG[blockIdx.x] = g;
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 // K2c variant and the number of per-CTA partial outputs (Z y, max |g|) it produces.
 // K2c variant (0 general, 1 staged ring, 2 streamed) and the number of per-CTA partial outputs (Z y, max |g|)
@@ -720,6 +776,26 @@ int launch_k2_producer(mcba_handle* h, const double* x, int loss, double f_scale
   if ((loss & 0xff) == kLossLinear) return launch_k2p_w<kLossLinear>(h, p);
   if (loss & kLossIrls) return launch_k2p_w<kLossSoftL1 | kLossIrls>(h, p);
   return launch_k2p_w<kLossSoftL1>(h, p);
+}
+
+// pose gradient and max |g| only (the closing evaluation of a solve); same partial-output count as K2c
+int launch_k2_gradient(mcba_handle* h, const double* x) {
+  const Layout& L = h->L;
+  K2CParams p{};
+  p.C = L.C;
+  p.F = L.F;
+  p.nTiles = L.nTiles;
+  p.H = h->d_H;
+  p.perm = h->d_perm;
+  p.active = h->d_active;
+  p.x = x;
+  p.cams = h->d_cams;
+  p.gpose = h->d_gpose;
+  p.partG = h->d_partG;
+  k2c_grad_kernel<<<h->n_part_c, 128, 0, h->stream>>>(p);
+  h->launches++;
+  MCBA_CUDA(cudaGetLastError());
+  return MCBA_OK;
 }
 
 int launch_k2_consumer(mcba_handle* h, const double* x, double lambda) {

@@ -126,6 +126,13 @@ static int evaluate(mcba_handle* h, const double* x, double lambda, int loss, do
 // part of d_red is left stale (nothing reads it before the next evaluation rebuilds it).
 static int evaluate_tail(mcba_handle* h, const double* x, double lambda, bool need_system = true) {
   int rc;
+  static const bool full_closing = getenv("MCBA_FULL_CLOSING_EVAL") != nullptr;   // A/B: K2c instead of the gradient kernel
+  if (!need_system && !full_closing) {
+    // gradient and cost only: the pose gradients come from a kernel that reads just the q_ext rows of the hand-off
+    // (no Z, no factor: b and S in d_red are left stale, nothing reads them before the next evaluation rebuilds them)
+    if ((rc = launch_k2_gradient(h, x))) return rc;
+    return finalize_and_sum(h);
+  }
   if ((rc = launch_k2_consumer(h, x, lambda))) return rc;
   if (need_system && (rc = launch_k2_syrk(h))) return rc;
   return finalize_and_sum(h);

@@ -178,6 +178,7 @@ int launch_predict(mcba_handle* h, const double* x, double* uv_out);
 int launch_cost(mcba_handle* h, const double* x, int loss, double f_scale, double* out_scal);
 int launch_k2_producer(mcba_handle* h, const double* x, int loss, double f_scale);
 int launch_k2_consumer(mcba_handle* h, const double* x, double lambda);
+int launch_k2_gradient(mcba_handle* h, const double* x);   // pose gradient only (closing evaluation)
 int k2_producer_grid(const mcba::Layout& L, int n_sm, int* warps);
 int k2_consumer_parts(const mcba::Layout& L, int n_sm, int* mode);
 int launch_k2_syrk(mcba_handle* h);
