@@ -584,6 +584,7 @@ struct HostPipe {
   double g_lambda = 0.0, g_f_scale = 0.0;
   int g_loss = -1;
   int same_params_calls = 0;          // consecutive calls with these values: a caller that varies lambda never captures
+  bool graphs_off = false;            // the stream could not be captured
   bool parent_stale = false;          // the last call's observations are in the children only
   double lambda = 0.0, f_scale = 1.0; // ... and so is its evaluation (re-run on the parent when it is needed)
   int loss = 0;
@@ -732,9 +733,15 @@ static int build_reduced_host_pipelined(mcba_handle* h, const double* h_uvs, con
     MCBA_CUDA(cudaStreamWaitEvent(h->stream, P.landed[k], 0));
     if (P.graphs[k]) {
       MCBA_CUDA(cudaGraphLaunch(P.graphs[k], h->stream));
-    } else if (P.warmed[k] && !no_graphs && P.same_params_calls >= 1) {
+    } else if (P.warmed[k] && !no_graphs && !P.graphs_off && P.same_params_calls >= 1) {
       cudaGraph_t graph = nullptr;
-      MCBA_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();          // e.g. the legacy default stream cannot be captured: kernel by kernel from now on
+        P.graphs_off = true;
+        if ((rc = range_work(k))) return rc;
+        MCBA_CUDA(cudaEventRecord(P.done[k], h->stream));
+        continue;
+      }
       rc = range_work(k);
       const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
       if (rc || ce != cudaSuccess || !graph) {   // not capturable on this driver: run it the plain way from now on
