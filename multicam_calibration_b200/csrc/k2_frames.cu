@@ -645,8 +645,8 @@ __global__ void __launch_bounds__(kW * 32, 1) k2c_rows_kernel(const K2CParams p)
 // The evaluation that closes a solve needs neither Z nor the factor: only the pose gradient
 // g_f = P'^T sum_c E'^T q_ext (and max |g|, the optimality).  One warp per frame tile reads the six q_ext rows of
 // every live camera straight from the hand-off (coalesced 256-byte rows): 10 % of K2c's reads, none of its writes.
-__global__ void __launch_bounds__(128) k2c_grad_kernel(const K2CParams p) {
-  __shared__ double s_g[4];
+__global__ void __launch_bounds__(256) k2c_grad_kernel(const K2CParams p) {
+  __shared__ double s_g[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kW = blockDim.x >> 5;
   const int C = p.C, nc = 12 * C;
   const unsigned cmask = C >= 32 ? 0xffffffffu : (1u << C) - 1u;
@@ -792,7 +792,7 @@ int launch_k2_gradient(mcba_handle* h, const double* x) {
   p.cams = h->d_cams;
   p.gpose = h->d_gpose;
   p.partG = h->d_partG;
-  k2c_grad_kernel<<<h->n_part_c, 128, 0, h->stream>>>(p);
+  k2c_grad_kernel<<<h->n_part_c, 256, 0, h->stream>>>(p);   // 8 warps: one tile per warp at 6 x 50,000 (296 CTAs)
   h->launches++;
   MCBA_CUDA(cudaGetLastError());
   return MCBA_OK;
